@@ -1,0 +1,26 @@
+"""inflatox_b200 - B200-native back-end for inflatox's grid-evaluation hot path.
+
+`import inflatox_b200 as inflatox` gives the names the reference package exports for this path
+(reference python/inflatox/__init__.py:20-40): `Compiler`, `CompilationArtifact`,
+`InflationModel`, `consistency_conditions` (`InflationCondition`, `GeneralisedAL`), `log_info`,
+`log_warn`.  The symbolic model builder (`InflationModelBuilder`, reference symbolic.py) is
+upstream of the hot path and is NOT re-implemented: build models with the reference package and
+hand them to `inflatox_b200.Compiler`, or load a pickled model with `InflationModel.load`.
+"""
+from .version import __abi_version__, __version__
+from .model import InflationModel
+from .compiler import CompilationArtifact, Compiler, UnsupportedFunctionError
+from . import consistency_conditions
+from .libinflx_rs import log_info, log_warn
+
+__all__ = [
+    "CompilationArtifact",
+    "Compiler",
+    "InflationModel",
+    "UnsupportedFunctionError",
+    "consistency_conditions",
+    "log_info",
+    "log_warn",
+    "__version__",
+    "__abi_version__",
+]

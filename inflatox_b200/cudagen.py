@@ -1,0 +1,529 @@
+"""CUDA code generator: one hash-consed model DAG (`cexpr.Dag`) -> sm_100a kernels.
+
+The reference evaluates five separately compiled C functions per grid point (reference
+src/anguelova.rs:110-119 -> src/hesse_bindings.rs:54-58, 213-231), each recomputing the metric,
+the Christoffel symbols and the gradient norm from scratch.  Here every function of the model
+lives in ONE DAG and each DAG node is evaluated once, at the *lowest rate at which it changes*:
+
+    class P  depends on the model parameters only        -> once per parameter vector
+    class R  depends on x[0] (and parameters)            -> once per grid ROW      (`inflx_rows`)
+    class C  depends on x[1] (and parameters)            -> once per thread (= per grid column,
+                                                            reused over INFLX_RPT rows)
+    class M  depends on both coordinates                 -> once per grid point
+
+A value crosses from a slower class to a faster one through a *frontier*: P-frontier values sit
+in `__constant__` memory (so they are free operands of the FP64 instructions), R-frontier values in
+a small global array `rc[row][k]` that every thread of a row reads with warp-uniform loads.  The
+operations, their operands and their order are exactly those of the C text, so hoisting changes
+no rounding: a node is the same IEEE operation wherever it is evaluated.
+
+For the test models this moves most of the work off the per-point path (d5: 911 DAG nodes, 169 of
+them class M; EGNO: 618 / 193), including every log / general pow.
+
+Kernels are generated per *group* of output functions (one cubin each), so an operation never
+pays for model functions it does not read:
+
+    cmp  V v00 v10 v11 |grad V|^2   complete_analysis (+ on-trajectory)
+    con  V v00 v10 v11              consistency_only, consistency_rapidturn_only (+ on-trajectory)
+    eps  V |grad V|^2               epsilon_v_only (+ on-trajectory)
+    bas  v (and w1, inner_prod)     flag_quantum_dif; basis validation
+    pot  V                          potential / potential_array
+    hes  v00 v01 v10 v11            hesse / hesse_array
+"""
+from __future__ import annotations
+
+import math
+import os
+
+from .cexpr import Dag, ParsedUnit
+
+_CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
+
+PC_CAPACITY = 7680  # doubles of __constant__ memory for P-frontier values (60 of the 64 KiB)
+MAX_FAST_POW = 64  # |exponent| up to which literal (half-)integer powers use the dd chains
+
+# fixed epilogue cost in flops (a8 as written = 46, a9 = 13; the rest counted the
+# same way: + - * / sqrt and every libm-class call = 1, abs/neg/compare = 0)
+EPILOGUE_FLOPS = {
+    "complete_analysis": 46,
+    "consistency_only": 13,
+    "consistency_rapidturn_only": 8,
+    "epsilon_v_only": 3,
+    "flag_quantum_dif": 0,
+    "potential": 0,
+    "hesse": 0,
+    "basis": 0,
+}
+
+# group -> (grid roots, extra point-only roots, grid ops, point ops)
+GROUPS = {
+    "cmp": (("V", "v00", "v10", "v11", "g2"), (), ("complete_analysis",), ("complete_analysis",)),
+    "con": (
+        ("V", "v00", "v10", "v11"),
+        (),
+        ("consistency_only", "consistency_rapidturn_only"),
+        ("consistency_only", "consistency_rapidturn_only"),
+    ),
+    "eps": (("V", "g2"), (), ("epsilon_v_only",), ("epsilon_v_only",)),
+    "bas": (("b0", "b1"), ("w0", "w1", "ip"), ("flag_quantum_dif",), ("basis",)),
+    "pot": (("V",), (), ("potential",), ("potential",)),
+    "hes": (("v00", "v01", "v10", "v11"), (), ("hesse",), ("hesse",)),
+}
+
+OUT_DOUBLES = {  # doubles (or bytes for the flag) written per point
+    "complete_analysis": 6, "consistency_only": 1, "consistency_rapidturn_only": 1,
+    "epsilon_v_only": 1, "flag_quantum_dif": 1, "potential": 1, "hesse": 4, "basis": 7,
+}  # fmt: skip
+
+
+def _lit(v: float) -> str:
+    if math.isnan(v):
+        return "(0.0/0.0)"
+    if math.isinf(v):
+        return "(1.0/0.0)" if v > 0 else "(-1.0/0.0)"
+    s = repr(float(v))
+    if "e" not in s and "." not in s and "n" not in s:
+        s += ".0"
+    return f"({s})" if v < 0 or (v == 0 and math.copysign(1, v) < 0) else s
+
+
+def _int_pow_mults(n: int) -> int:
+    n = abs(n)
+    if n <= 1:
+        return 0
+    return n.bit_length() - 1 + bin(n).count("1") - 1
+
+
+class ModelRoots:
+    """Names the DAG nodes of the model functions the hot path reads (reference
+    src/hesse_bindings.rs:195-232 `fns[0]=v00, fns[2]=v10, fns[3]=v11`; dylib.rs:163-183)."""
+
+    def __init__(self, unit: ParsedUnit):
+        f = unit.functions
+        need = ["V", "v00", "v01", "v10", "v11", "grad_norm_squared", "v", "w1", "inner_prod"]
+        missing = [n for n in need if n not in f]
+        if missing:
+            raise Exception(f"model source lacks the function(s) {missing}; is it a 2-field model?")
+        self.node = {
+            "V": f["V"].result,
+            "v00": f["v00"].result,
+            "v01": f["v01"].result,
+            "v10": f["v10"].result,
+            "v11": f["v11"].result,
+            "g2": f["grad_norm_squared"].result,
+            "b0": f["v"].outputs[0],
+            "b1": f["v"].outputs[1],
+            "w0": f["w1"].outputs[0],
+            "w1": f["w1"].outputs[1],
+            "ip": f["inner_prod"].result,
+        }
+
+
+class GroupProgram:
+    """Classification, frontiers, flop counts and CUDA text for one group of model functions."""
+
+    def __init__(self, dag: Dag, roots: ModelRoots, group: str, n_params: int):
+        self.dag = dag
+        self.group = group
+        self.n_params = n_params
+        grid_names, point_names, self.grid_ops, self.point_ops = GROUPS[group]
+        self.grid_roots = {n: roots.node[n] for n in grid_names}
+        self.point_roots = {n: roots.node[n] for n in grid_names + point_names}
+        self.all_nodes = dag.reachable(self.point_roots.values())
+        self.grid_nodes = dag.reachable(self.grid_roots.values())
+        self._classify()
+        self._frontiers()
+
+    # -- analysis ----------------------------------------------------------------------------
+    def _classify(self):
+        d = self.dag
+        dep: dict[int, int] = {}
+        for i in self.all_nodes:
+            n = d.nodes[i]
+            k = n[0]
+            if k == "x":
+                if n[1] > 1:
+                    raise Exception("the CUDA back-end evaluates 2-field models only")
+                dep[i] = 2 << n[1]
+            elif k == "p":
+                dep[i] = 1
+            elif k in ("v1", "v2"):
+                dep[i] = 8
+            elif k in ("c", "i"):
+                dep[i] = 0
+            elif k == "xd":
+                raise Exception("field velocities are not part of the grid-evaluation path")
+            else:
+                b = 0
+                for o in d.operands(i):
+                    b |= dep[o]
+                dep[i] = b
+        self.dep = dep
+
+    def klass(self, i: int) -> str:
+        m = self.dep[i]
+        if m & 8:
+            return "V"
+        if m == 0:
+            # an unfoldable call on constants (e.g. tgamma(2.5)) is evaluated with the parameters
+            return "P" if self.is_op(i) else "K"
+        if m == 1:
+            return "P"
+        if m in (2, 3):
+            return "R"
+        if m in (4, 5):
+            return "C"
+        return "M"
+
+    def _frontiers(self):
+        d = self.dag
+        users: dict[int, list[int]] = {}
+        for i in self.all_nodes:
+            for o in d.operands(i):
+                users.setdefault(o, []).append(i)
+        root_ids = set(self.point_roots.values())
+        self.p_frontier = [
+            i
+            for i in self.all_nodes
+            if self.klass(i) == "P"
+            and (i in root_ids or any(self.klass(u) != "P" for u in users.get(i, ())))
+        ]
+        grid_set = set(self.grid_nodes)
+        grid_root_ids = set(self.grid_roots.values())
+        self.r_frontier = [
+            i
+            for i in self.grid_nodes
+            if self.klass(i) == "R"
+            and (
+                i in grid_root_ids
+                or any(u in grid_set and self.klass(u) != "R" for u in users.get(i, ()))
+            )
+        ]
+        self.p_slot = {n: k for k, n in enumerate(self.p_frontier)}
+        self.r_slot = {n: k for k, n in enumerate(self.r_frontier)}
+
+    def is_op(self, i: int) -> bool:
+        return self.dag.nodes[i][0] in ("+", "-", "*", "/", "neg", "f")
+
+    def nodes_of(self, classes: str, within=None) -> list[int]:
+        src = self.all_nodes if within is None else within
+        return [i for i in src if self.is_op(i) and self.klass(i) in classes]
+
+    def flops(self, nodes) -> int:
+        """Algorithmic flops of `nodes` by the SURVEY.md 8(d) rule."""
+        d = self.dag
+        total = 0
+        for i in nodes:
+            n = d.nodes[i]
+            k = n[0]
+            if k in ("+", "-", "*", "/"):
+                total += 1
+            elif k == "f":
+                if n[1] == "pow" and d.is_const(n[3]) and float(d.cval(n[3])).is_integer():
+                    e = int(d.cval(n[3]))
+                    total += _int_pow_mults(e) + (1 if e < 0 else 0)
+                elif n[1] == "fabs":
+                    pass
+                else:
+                    total += 1
+        return total
+
+    def stats(self) -> dict:
+        g = self.grid_nodes
+        ops = [i for i in g if self.is_op(i)]
+        cnt = {c: len([i for i in ops if self.klass(i) == c]) for c in "PRCM"}
+        return {
+            "dag_ops": len(ops),
+            "class_ops": cnt,
+            "flops_model": self.flops(ops),
+            "flops_per_point_executed": self.flops([i for i in ops if self.klass(i) == "M"]),
+            "n_p_frontier": len(self.p_frontier),
+            "n_r_frontier": len(self.r_frontier),
+        }
+
+    # -- emission ----------------------------------------------------------------------------
+    def _ref(self, i: int, scope: dict[int, str]) -> str:
+        """C expression naming node `i` inside a kernel whose already-bound values are `scope`."""
+        if i in scope:
+            return scope[i]
+        n = self.dag.nodes[i]
+        if n[0] == "c":
+            return _lit(n[1])
+        if n[0] == "i":
+            return _lit(float(n[1]))
+        raise KeyError(f"node {i} {n} is not available in this scope")
+
+    def _expr(self, i: int, scope: dict[int, str]) -> str:
+        d = self.dag
+        n = d.nodes[i]
+        k = n[0]
+        if k in ("+", "-", "*", "/"):
+            return f"{self._ref(n[1], scope)} {k} {self._ref(n[2], scope)}"
+        if k == "neg":
+            return f"-{self._ref(n[1], scope)}"
+        if k == "f":
+            name = n[1]
+            args = [self._ref(a, scope) for a in n[2:]]
+            if name == "pow" and d.is_const(n[3]):
+                e = float(d.cval(n[3]))
+                if e.is_integer() and 1 <= abs(e) <= MAX_FAST_POW:
+                    e = int(e)
+                    fn = f"inflx_powi<{e}>" if e > 0 else f"inflx_powi_neg<{-e}>"
+                    return f"{fn}({args[0]})"
+                e2 = 2.0 * e
+                if e2.is_integer() and abs(e2) <= 2 * MAX_FAST_POW:
+                    e2 = int(e2)  # odd
+                    fn = f"inflx_powh<{(e2 - 1) // 2}>" if e2 > 0 else f"inflx_powh_neg<{(-e2 - 1) // 2}>"
+                    return f"{fn}({args[0]})"
+            return f"{name}({', '.join(args)})"
+        raise KeyError(f"cannot emit node {i}: {n}")
+
+    def _block(self, nodes: list[int], scope: dict[int, str], indent: str) -> str:
+        """SSA statements for `nodes` (topological order); extends `scope` with their names."""
+        out = []
+        for i in nodes:
+            if i in scope:
+                continue
+            out.append(f"{indent}const double t{i} = {self._expr(i, scope)};")
+            scope[i] = f"t{i}"
+        return "\n".join(out) + ("\n" if out else "")
+
+    def _leaf_scope(self, extra: dict[tuple, str]) -> dict[int, str]:
+        """Names for leaves; `extra` maps ('x',0) etc. to C identifiers."""
+        scope = {}
+        for i in self.all_nodes:
+            n = self.dag.nodes[i]
+            if (n[0], n[1]) in extra and n[0] in ("x", "p", "v1", "v2"):
+                scope[i] = extra[(n[0], n[1])]
+        return scope
+
+    def cuda_source(self, model_name: str) -> str:
+        with open(os.path.join(_CSRC, "inflx_device.cuh")) as fh:
+            device_header = fh.read()
+        npf, nrf = len(self.p_frontier), len(self.r_frontier)
+        src = [device_header]
+        src.append(f'\n// ===== generated: model "{model_name}", group "{self.group}" =====\n')
+        src.append(f"#define INFLX_NP {self.n_params}\n#define INFLX_NPF {npf}\n")
+        src.append(f"#define INFLX_NRF {nrf}\n#define INFLX_PC_CAP {PC_CAPACITY}\n")
+        src.append("__constant__ double inflx_pc[INFLX_PC_CAP];\n\n")
+
+        # ---- (1) parameter block: one thread per parameter vector ----
+        scope = self._leaf_scope({("p", k): f"p[{k}]" for k in range(self.n_params)})
+        body = self._block(self.nodes_of("P"), scope, "  ")
+        stores = "".join(
+            f"  pc[{k}] = {self._ref(n, scope)};\n" for n, k in self.p_slot.items()
+        )
+        src.append(
+            "extern \"C\" __global__ void inflx_params(const double* __restrict__ p_all, "
+            "double* __restrict__ pc_all, u32 n_vectors) {\n"
+            "  const u32 s = blockIdx.x * blockDim.x + threadIdx.x;\n"
+            "  if (s >= n_vectors) return;\n"
+            "  const double* __restrict__ p = p_all + (u64)s * INFLX_NP;\n"
+            "  double* __restrict__ pc = pc_all + (u64)s * INFLX_NPF;\n"
+            "  (void)p; (void)pc;\n" + body + stores + "}\n\n"
+        )
+
+        def pc_scope(sweep_expr: str) -> dict[int, str]:
+            return {n: f"inflx_pc[{sweep_expr}{k}]" for n, k in self.p_slot.items()}
+
+        # ---- (2) row block: one thread per (row, parameter vector) ----
+        scope = pc_scope("pbase + ")
+        scope.update(self._leaf_scope({("x", 0): "x0"}))
+        body = self._block(self.nodes_of("R", self.grid_nodes), scope, "  ")
+        stores = "".join(
+            f"  rr[{k}] = {self._ref(n, scope)};\n" for n, k in self.r_slot.items()
+        )
+        src.append(
+            "extern \"C\" __global__ void inflx_rows(double* __restrict__ rc, double of0, double dx0, "
+            "u64 row_begin, u32 n_rows) {\n"
+            "  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;\n"
+            "  if (i >= n_rows) return;\n"
+            "  const u32 pbase = blockIdx.y * INFLX_NPF;\n"
+            "  const double x0 = inflx_coord(row_begin + i, dx0, of0);\n"
+            "  double* __restrict__ rr = rc + ((u64)blockIdx.y * n_rows + i) * INFLX_NRF;\n"
+            "  (void)pbase; (void)x0; (void)rr;\n" + body + stores + "}\n\n"
+        )
+
+        # ---- (3) grid kernels: thread = column, walks INFLX_RPT rows ----
+        for op in self.grid_ops:
+            for sweep in (False, True):
+                src.append(self._grid_kernel(op, sweep))
+        # ---- (4) point kernels (on-trajectory / scalar entry points) ----
+        for op in self.point_ops:
+            src.append(self._point_kernel(op))
+        return "".join(src)
+
+    def _epilogue(self, op: str, val, point: str, indent: str) -> str:
+        """Statement(s) writing the result of `op` for the point with flat index `point`."""
+        if op == "complete_analysis":
+            return (
+                f"{indent}inflx_store6(out, {point}, inflx_op_complete({val('V')}, {val('v00')}, "
+                f"{val('v10')}, {val('v11')}, {val('g2')}));\n"
+            )
+        if op == "consistency_only":
+            return (
+                f"{indent}out[{point}] = inflx_op_consistency({val('V')}, {val('v00')}, "
+                f"{val('v10')}, {val('v11')});\n"
+            )
+        if op == "consistency_rapidturn_only":
+            return (
+                f"{indent}out[{point}] = inflx_op_rapidturn({val('V')}, {val('v00')}, "
+                f"{val('v10')}, {val('v11')});\n"
+            )
+        if op == "epsilon_v_only":
+            return f"{indent}out[{point}] = inflx_op_epsilon_v({val('V')}, {val('g2')});\n"
+        if op == "flag_quantum_dif":
+            return (
+                f"{indent}reinterpret_cast<unsigned char*>(out)[{point}] = "
+                f"inflx_op_flag({val('b0')}, {val('b1')}, aux);\n"
+            )
+        if op == "potential":
+            return f"{indent}out[{point}] = {val('V')};\n"
+        raise KeyError(op)
+
+    def _grid_kernel(self, op: str, sweep: bool) -> str:
+        name = f"inflx_grid_{op}" + ("_sweep" if sweep else "")
+        pbase = "pbase + " if sweep else ""
+        scope = {n: f"inflx_pc[{pbase}{k}]" for n, k in self.p_slot.items()}
+        scope.update(self._leaf_scope({("x", 1): "x1"}))
+        col_block = self._block(self.nodes_of("C", self.grid_nodes), scope, "  ")
+        # row-frontier loads (warp-uniform addresses) + the per-point block
+        loads = "".join(
+            f"    const double r{n} = __ldg(rr + {k});\n" for n, k in self.r_slot.items()
+        )
+        for n in self.r_slot:
+            scope[n] = f"r{n}"
+        mixed = self._block(self.nodes_of("M", self.grid_nodes), scope, "    ")
+
+        def val(rname: str) -> str:
+            return self._ref(self.grid_roots[rname], scope)
+
+        if op == "hesse":
+            # (2,2,N0,N1) component-major output (reference src/hesse_bindings.rs:150-192)
+            epi = "".join(
+                f"    out[{c}ull * comp_stride + point] = {val(nm)};\n"
+                for c, nm in enumerate(("v00", "v01", "v10", "v11"))
+            )
+        else:
+            epi = self._epilogue(op, val, "point", "    ")
+        return (
+            f"extern \"C\" __global__ void __launch_bounds__(INFLX_BLOCK) {name}("
+            "double* __restrict__ out, const double* __restrict__ rc, double of1, double dx1, "
+            "u32 n1, u32 n_rows, u64 comp_stride, double aux) {\n"
+            "  const u32 col = blockIdx.x * INFLX_BLOCK + threadIdx.x;\n"
+            "  if (col >= n1) return;\n"
+            + ("  const u32 s = blockIdx.z;\n  const u32 pbase = s * INFLX_NPF;\n" if sweep else "  const u32 s = 0;\n")
+            + "  const double x1 = inflx_coord(col, dx1, of1);\n"
+            "  (void)x1; (void)aux; (void)comp_stride; (void)rc;\n"
+            + col_block
+            + "  const u32 r0 = blockIdx.y * INFLX_RPT;\n"
+            "#pragma unroll 1\n"
+            "  for (u32 j = 0; j < INFLX_RPT; ++j) {\n"
+            "    const u32 i = r0 + j;\n"
+            "    if (i >= n_rows) break;\n"
+            "    const u64 rowid = (u64)s * n_rows + i;\n"
+            "    const double* __restrict__ rr = rc + rowid * INFLX_NRF;\n"
+            "    const u64 point = rowid * n1 + col;\n"
+            "    (void)rr;\n" + loads + mixed + epi + "  }\n}\n\n"
+        )
+
+    def _point_kernel(self, op: str) -> str:
+        """One thread per explicit field-space point (reference src/anguelova.rs:633-977 and the
+        scalar entry points src/lib.rs:309-339, 384-419): coordinates are loaded, not generated."""
+        scope = {n: f"inflx_pc[{k}]" for n, k in self.p_slot.items()}
+        scope.update(self._leaf_scope({("x", 0): "x0", ("x", 1): "x1"}))
+        roots = self.point_roots if op == "basis" else self.grid_roots
+        want = [r for nm, r in roots.items() if nm != "ip"]
+        nodes = [i for i in self.dag.reachable(want) if self.is_op(i) and self.klass(i) in "RCM"]
+        body = self._block(nodes, scope, "  ")
+
+        def val(rname: str) -> str:
+            return self._ref(roots[rname], scope)
+
+        pre = ""
+        if op == "hesse":
+            epi = "".join(
+                f"  out[k * 4 + {c}] = {val(nm)};\n"
+                for c, nm in enumerate(("v00", "v01", "v10", "v11"))
+            )
+        elif op == "basis":
+            # v, w1 and the three metric inner products (reference src/lib.rs:142-203)
+            pre = self._inner_function()
+            epi = (
+                f"  const double b0 = {val('b0')}, b1 = {val('b1')}, w0 = {val('w0')}, w1 = {val('w1')};\n"
+                "  out[k * 7 + 0] = b0; out[k * 7 + 1] = b1; out[k * 7 + 2] = w0; out[k * 7 + 3] = w1;\n"
+                "  out[k * 7 + 4] = inflx_inner(x0, x1, b0, b1, b0, b1);\n"
+                "  out[k * 7 + 5] = inflx_inner(x0, x1, b0, b1, w0, w1);\n"
+                "  out[k * 7 + 6] = inflx_inner(x0, x1, w0, w1, w0, w1);\n"
+            )
+        else:
+            epi = self._epilogue(op, val, "k", "  ")
+        return (
+            pre
+            + f"extern \"C\" __global__ void inflx_points_{op}(double* __restrict__ out, "
+            "const double* __restrict__ xs, u64 n, double aux) {\n"
+            "  const u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;\n"
+            "  if (k >= n) return;\n"
+            "  const double2 xx = reinterpret_cast<const double2*>(xs)[k];\n"
+            "  const double x0 = xx.x, x1 = xx.y;\n"
+            "  (void)x0; (void)x1; (void)aux;\n" + body + epi + "}\n\n"
+        )
+
+    def _inner_function(self) -> str:
+        """`inner_prod` (reference compiler.py:445-472) as a device function of the two vectors."""
+        scope = {n: f"inflx_pc[{k}]" for n, k in self.p_slot.items()}
+        scope.update(
+            self._leaf_scope({
+                ("x", 0): "x0", ("x", 1): "x1", ("v1", 0): "a0", ("v1", 1): "a1",
+                ("v2", 0): "c0", ("v2", 1): "c1",
+            })  # fmt: skip
+        )
+        root = self.point_roots["ip"]
+        nodes = [
+            i for i in self.dag.reachable([root]) if self.is_op(i) and self.klass(i) in "RCMV"
+        ]
+        body = self._block(nodes, scope, "  ")
+        return (
+            "__device__ __noinline__ double inflx_inner(double x0, double x1, double a0, double a1, "
+            "double c0, double c1) {\n  (void)x0; (void)x1; (void)a0; (void)a1; (void)c0; (void)c1;\n"
+            + body
+            + f"  return {self._ref(root, scope)};\n}}\n\n"
+        )
+
+
+class ModelProgram:
+    """All groups of one model + the metadata the artefact header carries."""
+
+    def __init__(self, unit: ParsedUnit):
+        if unit.dim != 2:
+            raise Exception(
+                f"the CUDA back-end evaluates 2-field models (the model has {unit.dim} fields)"
+            )
+        self.unit = unit
+        self.roots = ModelRoots(unit)
+        self.groups = {
+            g: GroupProgram(unit.dag, self.roots, g, unit.n_parameters or 0) for g in GROUPS
+        }
+
+    def flops_per_point(self, op: str) -> int:
+        """F(model, op) of SURVEY.md 8(d): joint-CSE DAG of the functions `op` reads + epilogue."""
+        for g, (_, _, grid_ops, point_ops) in GROUPS.items():
+            if op in grid_ops or op in point_ops:
+                gp = self.groups[g]
+                ops = [i for i in gp.grid_nodes if gp.is_op(i)]
+                return gp.flops(ops) + EPILOGUE_FLOPS[op]
+        raise KeyError(op)
+
+    def metadata(self) -> dict:
+        meta = {}
+        for g, gp in self.groups.items():
+            st = gp.stats()
+            st["grid_ops"] = list(gp.grid_ops)
+            st["point_ops"] = list(gp.point_ops)
+            meta[g] = st
+        flops = {}
+        for g, (_, _, grid_ops, point_ops) in GROUPS.items():
+            for op in set(grid_ops) | set(point_ops):
+                if op != "basis":
+                    flops[op] = self.flops_per_point(op)
+        return {"groups": meta, "flops_per_point": flops}

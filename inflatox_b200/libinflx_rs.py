@@ -1,0 +1,393 @@
+"""Drop-in for the reference's Rust extension module `inflatox.libinflx_rs`.
+
+Exports exactly the names the reference registers in its pyo3 module (reference
+src/lib.rs:68-92) with the same argument order, shapes and error classes, implemented as a thin
+ctypes binding of the C ABI in include/inflx_b200.h (engine: csrc/inflx_engine.cpp, CUDA driver
+API).  Caller-allocated numpy outputs are filled in place, as the reference does through
+`PyReadwriteArray*`.  `solve_eom_rk4` / `solve_eom_rkf` (the sequential background ODE solver,
+reference src/background_solver.rs) are outside the grid-evaluation path and raise
+NotImplementedError.
+"""
+from __future__ import annotations
+
+import ctypes
+import sys
+
+import numpy as np
+
+from . import _native
+
+__all__ = [
+    "InflatoxPyDyLib", "open_inflx_dylib", "log_info", "log_warn", "flag_quantum_dif_py",
+    "consistency_only", "consistency_rapidturn_only", "epsilon_v_only", "complete_analysis",
+    "complete_analysis_on_trajectory", "consistency_only_on_trajectory",
+    "consistency_rapidturn_only_on_trajectory", "epsilon_v_only_on_trajectory", "solve_eom_rk4",
+    "solve_eom_rkf", "PanicException", "pinned_empty", "sweep", "grid_eval",
+]  # fmt: skip
+
+_DP = ctypes.POINTER(ctypes.c_double)
+
+
+class PanicException(BaseException):
+    """Stands in for pyo3_runtime.PanicException: the reference `panic!`s on non-contiguous
+    arrays (reference src/anguelova.rs:189-191, 210-212)."""
+
+
+def log_info(msg: str) -> None:  # reference src/lib.rs:94-97
+    print(f"\033[1;35m[Inflatox Info]\033[0m\n{msg}", file=sys.stderr)
+
+
+def log_warn(msg: str) -> None:  # reference src/lib.rs:99-102
+    print(f"\033[1;33m[Inflatox Warning]\033[0m\n{msg}", file=sys.stderr)
+
+
+def _f64_in(a, what: str) -> np.ndarray:
+    """Read-only fp64 input.  Lists are accepted (more lenient than pyo3); an ndarray must be
+    C-contiguous like the reference demands."""
+    if isinstance(a, np.ndarray):
+        if a.dtype != np.float64:
+            raise TypeError(f"{what} must be a float64 array, got {a.dtype}")
+        if not a.flags.c_contiguous:
+            raise PanicException(f"{what.upper()} SHOULD BE C-CONTIGUOUS")
+        return a
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _out(a, dtype, what: str) -> np.ndarray:
+    if not isinstance(a, np.ndarray) or a.dtype != dtype:
+        raise TypeError(f"{what} must be a numpy array of dtype {np.dtype(dtype)}")
+    if not a.flags.c_contiguous:
+        raise PanicException("OUTPUT ARRAY SHOULD BE C-CONTIGUOUS")
+    if not a.flags.writeable:
+        raise TypeError(f"{what} is read-only")
+    return a
+
+
+def _dptr(a: np.ndarray):
+    return a.ctypes.data_as(_DP)
+
+
+def _ss(start_stop) -> np.ndarray:
+    ss = _f64_in(start_stop, "start_stop array")
+    if ss.ndim != 2:
+        raise TypeError("start_stop must be a 2D float64 array")
+    return ss
+
+
+class InflatoxPyDyLib:
+    """Handle of an opened model artefact (reference src/lib.rs:104-106, methods :205-463)."""
+
+    def __init__(self, handle: ctypes.c_void_p, path: str):
+        self._h = handle
+        self.path = path
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                _native.lib().inflx_close(h)
+            except Exception:
+                pass
+
+    # -- metadata -----------------------------------------------------------------------------
+    @property
+    def n_fields(self) -> int:
+        return int(_native.lib().inflx_n_fields(self._h))
+
+    @property
+    def n_parameters(self) -> int:
+        return int(_native.lib().inflx_n_parameters(self._h))
+
+    @property
+    def name(self) -> str:
+        return _native.lib().inflx_model_name(self._h).decode()
+
+    def set_devices(self, ordinals) -> None:
+        arr = (ctypes.c_int * len(ordinals))(*ordinals)
+        _native.raise_for_status(_native.lib().inflx_set_devices(self._h, arr, len(ordinals)))
+
+    def devices(self) -> list[int]:
+        buf = (ctypes.c_int * 64)()
+        n = _native.lib().inflx_get_devices(self._h, buf, 64)
+        return [buf[i] for i in range(min(n, 64))]
+
+    # -- reference methods --------------------------------------------------------------------
+    def validate_basis_on_domain(self, num_points, p, start_stop, accuracy) -> None:
+        num_points = np.ascontiguousarray(num_points, dtype=np.uint32)
+        p, ss = _f64_in(p, "parameter array"), _ss(start_stop)
+        rc = _native.lib().inflx_validate_basis_on_domain(
+            self._h, num_points.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), num_points.size,
+            _dptr(p), p.size, _dptr(ss), ss.shape[0], ss.shape[1], float(accuracy),
+        )  # fmt: skip
+        _native.raise_for_status(rc)
+
+    def potential(self, x, p) -> float:
+        x, p = _f64_in(x, "field-space array"), _f64_in(p, "parameter array")
+        if x.ndim != 1 or p.ndim != 1:
+            x_len = x.size if x.ndim == 1 else 0  # forces the reference's Shape error
+            p_len = p.size if p.ndim == 1 else (1 << 62)
+        else:
+            x_len, p_len = x.size, p.size
+        val = ctypes.c_double()
+        rc = _native.lib().inflx_potential(
+            self._h, _dptr(x), x_len, _dptr(p), p_len, ctypes.byref(val)
+        )
+        _native.raise_for_status(rc)
+        return val.value
+
+    def potential_array(self, x, p, start_stop) -> None:
+        x = _out(x, np.float64, "x")
+        p, ss = _f64_in(p, "parameter array"), _ss(start_stop)
+        if x.ndim != self.n_fields:  # reference src/lib.rs:355-363
+            raise Exception(
+                f"Expected array with shape [], received array with shape {list(x.shape)}. "
+                "Context: expected an array with with the same number of axes as there are "
+                "field-space coordinates"
+            )
+        rc = _native.lib().inflx_potential_array(
+            self._h, _dptr(x), x.shape[0], x.shape[1], _dptr(p), p.size, _dptr(ss), ss.shape[0],
+            ss.shape[1],
+        )  # fmt: skip
+        _native.raise_for_status(rc)
+
+    def hesse(self, x, p) -> np.ndarray:
+        x, p = _f64_in(x, "field-space array"), _f64_in(p, "parameter array")
+        out = np.zeros((2, 2), dtype=np.float64)
+        rc = _native.lib().inflx_hesse(self._h, _dptr(x), x.size, _dptr(p), p.size, _dptr(out))
+        _native.raise_for_status(rc)
+        return out
+
+    def hesse_array(self, nx, p, start_stop) -> np.ndarray:
+        nx = np.atleast_1d(np.asarray(nx)).astype(np.int64)
+        p, ss = _f64_in(p, "parameter array"), _ss(start_stop)
+        if nx.size != self.n_fields:  # reference src/lib.rs:437-444
+            raise Exception(
+                f"Expected array with shape [{self.n_fields}], received array with shape "
+                f"[{nx.size}]. Context: expected a 1D array with as many elements as there are "
+                "field-space coordinates"
+            )
+        out = np.zeros((2, 2, int(nx[0]), int(nx[1])), dtype=np.float64)
+        rc = _native.lib().inflx_hesse_array(
+            self._h, _dptr(out), int(nx[0]), int(nx[1]), _dptr(p), p.size, _dptr(ss), ss.shape[0],
+            ss.shape[1],
+        )  # fmt: skip
+        _native.raise_for_status(rc)
+        return out
+
+
+def open_inflx_dylib(lib_path: str, check_basis: bool) -> InflatoxPyDyLib:
+    """reference src/lib.rs:108-115"""
+    h = ctypes.c_void_p()
+    rc = _native.lib().inflx_open(str(lib_path).encode(), int(bool(check_basis)), ctypes.byref(h))
+    _native.raise_for_status(rc)
+    return InflatoxPyDyLib(h, str(lib_path))
+
+
+# ----------------------------------------------------------------------------------------------
+# grid pyfunctions (reference src/anguelova.rs:176-550, 569-626)
+# ----------------------------------------------------------------------------------------------
+def _grid2(fn_name: str, lib, p, out, start_stop, progress, threads) -> None:
+    p, ss = _f64_in(p, "parameter array"), _ss(start_stop)
+    out = _out(out, np.float64, "out")
+    if out.ndim != 2:
+        raise TypeError("out must be a 2D float64 array")
+    rc = getattr(_native.lib(), fn_name)(
+        lib._h, _dptr(p), p.size, _dptr(out), out.shape[0], out.shape[1], _dptr(ss), ss.shape[0],
+        ss.shape[1], int(bool(progress)), int(threads),
+    )  # fmt: skip
+    _native.raise_for_status(rc)
+
+
+def consistency_only(lib, p, out, start_stop, progress, threads) -> None:
+    _grid2("inflx_consistency_only", lib, p, out, start_stop, progress, threads)
+
+
+def consistency_rapidturn_only(lib, p, out, start_stop, progress, threads) -> None:
+    _grid2("inflx_consistency_rapidturn_only", lib, p, out, start_stop, progress, threads)
+
+
+def epsilon_v_only(lib, p, out, start_stop, progress, threads) -> None:
+    _grid2("inflx_epsilon_v_only", lib, p, out, start_stop, progress, threads)
+
+
+def complete_analysis(lib, p, out, start_stop, progress, threads) -> None:
+    p, ss = _f64_in(p, "parameter array"), _ss(start_stop)
+    out = _out(out, np.float64, "out")
+    if out.ndim != 3:
+        raise TypeError("out must be a 3D float64 array")
+    rc = _native.lib().inflx_complete_analysis(
+        lib._h, _dptr(p), p.size, _dptr(out), out.shape[0], out.shape[1], out.shape[2], _dptr(ss),
+        ss.shape[0], ss.shape[1], int(bool(progress)), int(threads),
+    )  # fmt: skip
+    _native.raise_for_status(rc)
+
+
+def flag_quantum_dif_py(lib, p, x, start_stop, progress, accuracy) -> None:
+    p, ss = _f64_in(p, "parameter array"), _ss(start_stop)
+    x = _out(x, np.bool_, "x")
+    if x.ndim != 2:
+        raise TypeError("x must be a 2D bool array")
+    rc = _native.lib().inflx_flag_quantum_dif(
+        lib._h, _dptr(p), p.size, x.ctypes.data_as(ctypes.c_void_p), x.shape[0], x.shape[1],
+        _dptr(ss), ss.shape[0], ss.shape[1], int(bool(progress)), float(accuracy),
+    )  # fmt: skip
+    _native.raise_for_status(rc)
+
+
+# ----------------------------------------------------------------------------------------------
+# on-trajectory pyfunctions (reference src/anguelova.rs:633-977)
+# ----------------------------------------------------------------------------------------------
+def _traj_x(x) -> np.ndarray:
+    x = _f64_in(x, "field-space array")
+    if x.ndim != 2:
+        raise TypeError("x must be a 2D float64 array")
+    return x
+
+
+def complete_analysis_on_trajectory(lib, p, x, out, progress, threads) -> None:
+    p, x = _f64_in(p, "parameter array"), _traj_x(x)
+    out = _out(out, np.float64, "out")
+    if out.ndim != 2:
+        raise TypeError("out must be a 2D float64 array")
+    rc = _native.lib().inflx_complete_analysis_on_trajectory(
+        lib._h, _dptr(p), p.size, _dptr(x), x.shape[0], x.shape[1], _dptr(out), out.shape[0],
+        out.shape[1], int(bool(progress)), int(threads),
+    )  # fmt: skip
+    _native.raise_for_status(rc)
+
+
+def _traj1(fn_name: str, lib, p, x, out, progress, threads) -> None:
+    p, x = _f64_in(p, "parameter array"), _traj_x(x)
+    out = _out(out, np.float64, "out")
+    if out.ndim != 1:
+        raise TypeError("out must be a 1D float64 array")
+    rc = getattr(_native.lib(), fn_name)(
+        lib._h, _dptr(p), p.size, _dptr(x), x.shape[0], x.shape[1], _dptr(out), out.shape[0],
+        int(bool(progress)), int(threads),
+    )  # fmt: skip
+    _native.raise_for_status(rc)
+
+
+def consistency_only_on_trajectory(lib, p, x, out, progress, threads) -> None:
+    _traj1("inflx_consistency_only_on_trajectory", lib, p, x, out, progress, threads)
+
+
+def consistency_rapidturn_only_on_trajectory(lib, p, x, out, progress, threads) -> None:
+    _traj1("inflx_consistency_rapidturn_only_on_trajectory", lib, p, x, out, progress, threads)
+
+
+def epsilon_v_only_on_trajectory(lib, p, x, out, progress, threads) -> None:
+    _traj1("inflx_epsilon_v_only_on_trajectory", lib, p, x, out, progress, threads)
+
+
+def solve_eom_rk4(*args, **kwargs):
+    raise NotImplementedError(
+        "the background ODE solver (reference src/background_solver.rs) is a sequential CPU "
+        "integrator outside the grid-evaluation path this package accelerates"
+    )
+
+
+solve_eom_rkf = solve_eom_rk4
+
+
+# ----------------------------------------------------------------------------------------------
+# extensions: pinned outputs, fused parameter sweep, row shards, device-resident output
+# ----------------------------------------------------------------------------------------------
+class _PinnedBlock:
+    """Owner of one cuMemHostAlloc block; freed when the last numpy view dies."""
+
+    def __init__(self, nbytes: int):
+        ptr = ctypes.c_void_p()
+        _native.raise_for_status(_native.lib().inflx_host_alloc(nbytes, ctypes.byref(ptr)))
+        self.ptr, self.nbytes = ptr, nbytes
+
+    def __del__(self):
+        p, self.ptr = getattr(self, "ptr", None), None
+        if p:
+            try:
+                _native.lib().inflx_host_free(p)
+            except Exception:
+                pass
+
+
+_pin_pool: dict[int, list[_PinnedBlock]] = {}
+
+
+class _PinnedLease:
+    """Returns the block to the pool (instead of unpinning it) when the array is collected."""
+
+    def __init__(self, block: _PinnedBlock):
+        self.block = block
+
+    def __del__(self):
+        pool = _pin_pool.setdefault(self.block.nbytes, [])
+        if len(pool) < 4:
+            pool.append(self.block)
+
+
+def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
+    """numpy array in page-locked host memory (pooled: pinning costs more than the kernels).
+    Outputs allocated here are written by DMA straight from the GPU(s)."""
+    shape = tuple(int(s) for s in (shape if hasattr(shape, "__len__") else (shape,)))
+    nbytes = max(1, int(np.prod(shape)) * np.dtype(dtype).itemsize)
+    nbytes = (nbytes + (1 << 21) - 1) & ~((1 << 21) - 1)
+    pool = _pin_pool.get(nbytes)
+    block = pool.pop() if pool else _PinnedBlock(nbytes)
+    lease = _PinnedLease(block)
+    buf = (ctypes.c_char * nbytes).from_address(block.ptr.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    # keep the lease alive as long as any view of the buffer exists
+    buf._inflx_lease = lease
+    return arr
+
+
+def grid_eval(lib, op: str, p, out, n0: int, n1: int, start_stop, rows=None, accuracy: float = 0.0,
+              device: int = -1, out_device_ptr: int | None = None, stream: int | None = None):  # fmt: skip
+    """Extended grid interface (inflx_grid_eval): row shard `rows=(begin,end)` with global
+    coordinates, parameter sweep (`p` of shape (S,P)), optional device-resident output.  Returns
+    the engine's report as a dict."""
+    p = _f64_in(p, "parameter array")
+    p2 = p.reshape(1, -1) if p.ndim == 1 else p
+    if p2.shape[1] != lib.n_parameters:
+        raise Exception(
+            f"Expected array with shape [2], received array with shape [{p2.shape[1]}]. "
+            f'Context: model "{lib.name}" has {lib.n_parameters} paramters'
+        )
+    ss = np.ascontiguousarray(start_stop, dtype=np.float64).reshape(4)
+    r0, r1 = rows if rows is not None else (0, n0)
+    rq = _native.GridRequest()
+    rq.op = _native.OPS[op]
+    rq.params = _dptr(p2)
+    rq.n_vectors = p2.shape[0]
+    rq.n0, rq.n1 = n0, n1
+    rq.start_stop = (ctypes.c_double * 4)(*ss)
+    rq.row_begin, rq.row_end = r0, r1
+    rq.aux = accuracy
+    if out_device_ptr is not None:
+        rq.out = ctypes.c_void_p(out_device_ptr)
+        rq.out_is_device = 1
+        rq.stream = ctypes.c_void_p(stream or 0)
+    else:
+        per = {"complete_analysis": 6, "hesse": 4}.get(op, 1)
+        need = p2.shape[0] * (r1 - r0) * n1 * per
+        if not isinstance(out, np.ndarray) or not out.flags.c_contiguous or out.size != need:
+            raise TypeError(f"out must be a C-contiguous array of {need} elements")
+        rq.out = out.ctypes.data_as(ctypes.c_void_p)
+        rq.out_is_device = 0
+    rq.device = device
+    rep = _native.GridReport()
+    _native.raise_for_status(
+        _native.lib().inflx_grid_eval(lib._h, ctypes.byref(rq), ctypes.byref(rep))
+    )
+    return {
+        "kernel_ms": rep.kernel_ms, "total_ms": rep.total_ms, "launches": int(rep.launches),
+        "d2h_bytes": int(rep.d2h_bytes), "h2d_bytes": int(rep.h2d_bytes),
+        "n_devices": rep.n_devices,
+    }  # fmt: skip
+
+
+def sweep(lib, op: str, params, out, start_stop, accuracy: float = 0.0):
+    """Fused parameter sweep: `params` (S,P), `out` (S,N0,N1[,6]); the sweep axis is part of the
+    launch grid (BASELINE config C5)."""
+    n0, n1 = out.shape[1], out.shape[2]
+    return grid_eval(lib, op, params, out, n0, n1, start_stop, accuracy=accuracy)
