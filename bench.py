@@ -1,0 +1,393 @@
+#!/usr/bin/env python3
+"""bench.py - throughput of the grid-evaluation hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--config C1..C5] [--impl reference]
+
+A "step" is one pass of the hot path over the configured grid.  Default workload: BASELINE
+config C3 (EGNO model, complete_analysis, 16384 x 16384 grid, rows sharded over the N ranks - the
+configuration the metric "fp64 grid points/s for complete_analysis at 1/2/4/8 B200" is quoted on;
+12.9 GB of output per step, so every step streams far more than the 126 MB L2 and no flush is
+needed).  One process per GPU (torchrun for N > 1); no data-path collective exists - the only
+torch.distributed traffic is the barrier and the max-over-ranks of the timings.
+
+    value      points/s with the output left in HBM (device-resident), timed with CUDA events on
+               the launching stream; max over ranks of the summed step times
+    e2e        points/s through the reference-facing C-ABI call with HOST (pinned numpy) output:
+               H2D of the parameters + kernels + D2H of the result inside the timed region
+    roofline   dominant kernel (inflx_grid_complete_analysis): algorithmic flops per point
+               (frozen in the artefact) x points / CUDA-event duration, against the
+               FP64 FMA peak measured in this run (MEASURED_PEAKS.json has no fp64 entry); the HBM
+               write roofline (48 B/point, peak from MEASURED_PEAKS.json) is reported beside it
+    cpu_baseline  the oracle (restated reference path, gcc + OpenMP over all host cores) timed on
+               a bounded row sample of the same grid (N=1, rank 0)
+
+--impl reference times that same CPU path as the reference arm (the reference's Rust crate cannot
+be built here: no rustc/cargo).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+os.environ.setdefault("INFLATOX_CACHE_DIR", os.path.join(ROOT, "tests", ".cubin_cache"))
+os.environ.setdefault("INFLATOX_QUIET", "1")
+
+import numpy as np  # noqa: E402
+
+CONFIGS = {
+    # id: (model, op, N0, N1, sweep vectors)
+    "C1": ("hyper", "complete_analysis", 1000, 1000, 1),
+    "C2": ("angular", "consistency_only", 4096, 4096, 1),
+    "C3": ("egno", "complete_analysis", 16384, 16384, 1),
+    "C4": ("d5", "complete_analysis", 16384, 16384, 1),
+    "C5": ("hyper", "complete_analysis", 1024, 1024, 1024),
+}
+OUT_DOUBLES = {"complete_analysis": 6, "consistency_only": 1}
+
+
+def workload(cfg: str):
+    import cases
+
+    model, op, n0, n1, S = CONFIGS[cfg]
+    ext = cases.EXTENT[model]
+    if S == 1:
+        p = cases.params(model).reshape(1, -1)
+    else:
+        # BASELINE C5: rng(0); L~U(0.05,2), m~10^U(-3,1), phi0~U(-1,1), placed through the
+        # symbol dictionary (args order of the hyperinflation model: m, phi0, L)
+        rng = np.random.default_rng(0)
+        L = rng.uniform(0.05, 2.0, S)
+        m = 10.0 ** rng.uniform(-3.0, 1.0, S)
+        phi0 = rng.uniform(-1.0, 1.0, S)
+        p = np.ascontiguousarray(np.stack([m, phi0, L], axis=1))
+    return model, op, n0, n1, S, ext, p
+
+
+class ClockSampler:
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.reasons = index, [], set()
+        self.max_mhz, self._stop, self._t = None, threading.Event(), None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unsampled"]}
+        return {
+            "sm_mhz": float(np.median(self.samples)),
+            "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons),
+            "samples": len(self.samples),
+        }
+
+
+def cpu_rate(model, op, n0, n1, ext, p, seconds, threads=0):
+    """points/s of the restated reference CPU path on a bounded row sample (~`seconds`)."""
+    import oracle
+
+    orc = oracle.Oracle(model)
+    fn = getattr(orc, op)
+    probe_rows = max(1, min(n0, (1 << 20) // n1))
+    t0 = time.perf_counter()
+    fn(p, n0, n1, ext, rows=(0, probe_rows), threads=threads)
+    dt = max(time.perf_counter() - t0, 1e-4)
+    rows = int(min(n0, max(probe_rows, probe_rows * seconds / dt)))
+    r0 = (n0 - rows) // 2
+    t0 = time.perf_counter()
+    fn(p, n0, n1, ext, rows=(r0, r0 + rows), threads=threads)
+    dt = time.perf_counter() - t0
+    return rows * n1 / dt, rows, r0, dt
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    model, op, n0, n1, S, ext, p = workload(a.config)
+    cores = os.cpu_count() or 1
+    per_step = []
+    rows = r0 = 0
+    for i in range(a.warmup + a.steps):
+        rate, rows, r0, dt = cpu_rate(model, op, n0, n1, ext, p[0], a.ref_seconds)
+        if i >= a.warmup:
+            per_step.append((rows * n1, dt))
+    pts = sum(x for x, _ in per_step)
+    tt = sum(t for _, t in per_step)
+    value = pts / tt
+    sample = f"rows [{r0},{r0 + rows}) of the {n0}x{n1} grid per step ({rows * n1} points)"
+    line = {
+        "impl": "reference", "metric": "grid_points_per_s", "value": value, "unit": "points/s",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": 1e3 * tt / max(1, a.steps), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(a.config, model, op, n0, n1, S, a.gpus),
+        "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }  # fmt: skip
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(cfg, model, op, n0, n1, S, gpus):
+    return {
+        "workload": f"{cfg}: {model} model, {op}, {n0}x{n1} grid"
+        + (f", {S} parameter vectors (fused sweep)" if S > 1 else "")
+        + ", extent and parameters of the reference's own test for this model",
+        "grid": [n0, n1],
+        "n_vectors": S,
+        "sharding": f"rows/{gpus}" if S < gpus or S == 1 else f"vectors/{gpus}",
+        "l2": "outputs per step exceed the 126 MB L2; no flush" if n0 * n1 * S * 48 > (1 << 28)
+        else "L2 flushed between timed steps (256 MB memset)",
+        "mode": "strict (--fmad=false, IEEE div/sqrt)",
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C3", choices=sorted(CONFIGS))
+    ap.add_argument("--ref-seconds", type=float, default=8.0, help="CPU seconds per reference step")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU baseline sample size")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        return run_reference(a)
+
+    import torch
+    import torch.distributed as dist
+
+    import cases
+    from inflatox_b200 import _native
+    from inflatox_b200 import libinflx_rs as rs
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fall-back exists)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v: float) -> float:
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    model, op, n0, n1, S, ext, p = workload(a.config)
+    art = cases.artifact(model)
+    lib = rs.open_inflx_dylib(art.shared_object_path, False)
+    lib.set_devices([local])
+    per = OUT_DOUBLES[op]
+    F = art.flops_per_point(op)
+    ss = np.array(ext, dtype=np.float64)
+
+    # shard: rows when a single vector, vectors for the sweep
+    if S == 1:
+        r0, r1 = n0 * rank // world, n0 * (rank + 1) // world
+        p_local = p
+    else:
+        r0, r1 = 0, n0
+        p_local = np.ascontiguousarray(p[S * rank // world : S * (rank + 1) // world])
+    S_local = p_local.shape[0]
+    my_points = S_local * (r1 - r0) * n1
+    total_points = S * n0 * n1
+
+    # ---- device-resident throughput (value) + dominant-kernel time ---------------------------
+    d_out = torch.empty(my_points * per, dtype=torch.float64, device="cuda")
+    small = my_points * per * 8 <= (1 << 28)
+    flush = torch.empty(1 << 28, dtype=torch.uint8, device="cuda") if small else None
+
+    def step_device():
+        if flush is not None:
+            flush.fill_(1)
+            torch.cuda.synchronize()
+        return rs.grid_eval(lib, op, p_local, None, n0, n1, ss, rows=(r0, r1), device=local,
+                            out_device_ptr=d_out.data_ptr())  # fmt: skip
+
+    for _ in range(a.warmup):
+        step_device()
+    launches0 = int(_native.lib().inflx_kernel_launches())
+    barrier()
+    with ClockSampler(local) as clocks:
+        ms, grid_ms = 0.0, 0.0
+        for _ in range(a.steps):
+            rep = step_device()
+            ms += rep["kernel_ms"]
+            grid_ms += rep["grid_ms"]
+        barrier()
+    launches = int(_native.lib().inflx_kernel_launches()) - launches0
+    ms = max_over_ranks(ms)
+    grid_ms_max = max_over_ranks(grid_ms)
+    value = total_points * a.steps / (ms / 1e3)
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------------
+    best = ctypes_double()
+    med = ctypes_double()
+    _native.raise_for_status(_native.lib().inflx_measure_fp64_peak(local, 5, best, med))
+    fp64_peak = best.value
+    per_launch_s = grid_ms / a.steps / 1e3
+    achieved_tf = F * my_points / per_launch_s / 1e12
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peaks = json.load(fh)
+    except OSError:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+    achieved_gbs = my_points * per * 8 / per_launch_s / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as fh:
+            traffic = json.load(fh).get(f"{a.config}")
+    roofline = {
+        "bound": "fp64", "kernel": f"inflx_grid_{op}", "achieved": achieved_tf, "peak": fp64_peak,
+        "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak, "traffic": traffic,
+        "flops_per_point": F, "points_per_launch": my_points,
+        "peak_source": "DFMA micro-kernel measured in this run (inflx_measure_fp64_peak; "
+        f"median {med.value:.2f}); MEASURED_PEAKS.json has no fp64 entry",
+        "note": "algorithmic flops (joint-CSE DAG + epilogue, SURVEY 8d) - parameter-only and "
+        "row-only sub-expressions are counted per point although they are hoisted",
+    }  # fmt: skip
+    roofline_hbm = {
+        "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+        "frac": achieved_gbs / hbm_peak, "bytes_per_point": per * 8, "peak_source": hbm_src,
+    }  # fmt: skip
+    del d_out, flush
+    torch.cuda.empty_cache()
+
+    # ---- end to end through the C-ABI call with host buffers -------------------------------------
+    e2e = None
+    if not a.no_e2e:
+        shape = (S_local, r1 - r0, n1, per) if per > 1 else (S_local, r1 - r0, n1)
+        h_out = rs.pinned_empty(shape)
+        single = world == 1 and S == 1
+
+        def step_host():
+            if single:  # exactly the reference-facing call
+                arr = h_out.reshape(n0, n1, per) if per > 1 else h_out.reshape(n0, n1)
+                fn = rs.complete_analysis if op == "complete_analysis" else rs.consistency_only
+                t0 = time.perf_counter()
+                fn(lib, p[0], arr, ss.reshape(2, 2), False, 0)
+                return (time.perf_counter() - t0) * 1e3
+            rep = rs.grid_eval(lib, op, p_local, h_out.reshape(-1), n0, n1, ss, rows=(r0, r1),
+                               device=local)  # fmt: skip
+            return rep["total_ms"]
+
+        for _ in range(max(1, min(a.warmup, 2))):
+            step_host()
+        barrier()
+        e_ms = sum(step_host() for _ in range(a.steps))
+        barrier()
+        e_ms = max_over_ranks(e_ms)
+        e2e = {
+            "value": total_points * a.steps / (e_ms / 1e3), "unit": "points/s",
+            "h2d_bytes_per_step": int(p_local.size * 8),
+            "d2h_bytes_per_step": int(my_points * per * 8),
+            "ms_per_step": e_ms / a.steps,
+            "api": "inflatox_b200.libinflx_rs.complete_analysis(lib, p, out, start_stop, progress, "
+            "threads) -> inflx_complete_analysis (C ABI)" if single else "inflx_grid_eval (C ABI, row/vector shard)",
+            "host_buffer": "pinned numpy (inflx_host_alloc pool), written by DMA",
+        }  # fmt: skip
+        del h_out
+
+    # ---- CPU baseline (rank 0, N=1) ------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu:
+        rate, rows, rr0, dt = cpu_rate(model, op, n0, n1, ext, p[0], a.cpu_seconds)
+        cpu = {
+            "value": rate, "unit": "points/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"rows [{rr0},{rr0 + rows}) of the {n0}x{n1} grid ({rows * n1} points, "
+            f"{dt:.1f} s), restated reference path (gcc -O3 -march=native + OpenMP, all cores)",
+        }  # fmt: skip
+
+    if rank == 0:
+        line = {
+            "metric": "grid_points_per_s", "value": value, "unit": "points/s", "n_gpus": world,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": config_dict(a.config, model, op, n0, n1, S, world),
+            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches,
+            "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu,
+            "dominant_kernel_ms_per_step": grid_ms_max / a.steps,
+        }  # fmt: skip
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def ctypes_double():
+    import ctypes
+
+    return ctypes.c_double()
+
+
+if __name__ == "__main__":
+    main()

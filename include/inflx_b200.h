@@ -170,6 +170,8 @@ typedef struct {
 typedef struct {
   double kernel_ms;       /* device time of the grid kernels of this call (CUDA events, max over
                              devices) */
+  double grid_ms;         /* out_is_device only: first grid-kernel launch -> last one done, i.e. the
+                             dominant kernel without the parameter/row pre-passes */
   double total_ms;        /* host wall time of the call */
   uint64_t launches;      /* kernels launched by this call */
   uint64_t d2h_bytes;     /* bytes copied device -> host */
@@ -189,6 +191,11 @@ inflx_status inflx_points_eval(inflx_lib *lib, int op, const double *p, const do
  * ring + parallel memcpy. */
 inflx_status inflx_host_alloc(size_t bytes, void **ptr);
 inflx_status inflx_host_free(void *ptr);
+
+/* ---- measurement support: sustained FP64 FMA rate (2 flop per DFMA) of one device, from a
+ * register-resident DFMA micro-kernel; the roofline denominator MEASURED_PEAKS.json lacks. */
+inflx_status inflx_measure_fp64_peak(int device, int repeats, double *tflops_best,
+                                     double *tflops_median);
 
 /* ---- introspection --------------------------------------------------------------------------- */
 int inflx_device_count(void);            /* -1 when no CUDA driver is present */

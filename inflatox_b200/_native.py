@@ -85,6 +85,7 @@ class GridRequest(ctypes.Structure):
 class GridReport(ctypes.Structure):
     _fields_ = [
         ("kernel_ms", ctypes.c_double),
+        ("grid_ms", ctypes.c_double),
         ("total_ms", ctypes.c_double),
         ("launches", ctypes.c_uint64),
         ("d2h_bytes", ctypes.c_uint64),
@@ -139,6 +140,7 @@ def _declare(lib: ctypes.CDLL) -> None:
     ]  # fmt: skip
     lib.inflx_grid_eval.argtypes = [vp, c.POINTER(GridRequest), c.POINTER(GridReport)]
     lib.inflx_points_eval.argtypes = [vp, ci, dp, dp, c.c_uint64, c.c_double, dp]
+    lib.inflx_measure_fp64_peak.argtypes = [ci, ci, dp, dp]
     lib.inflx_host_alloc.argtypes = [sz, c.POINTER(vp)]
     lib.inflx_host_free.argtypes = [vp]
 

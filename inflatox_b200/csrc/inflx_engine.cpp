@@ -5,6 +5,7 @@
 // kernels), the rayon grid drivers of src/anguelova.rs:173-550 (-> launch + row/parameter
 // sharding over the GPUs of one box + pipelined device->host copies) and the checks/messages of
 // src/lib.rs:117-463 and src/err.rs.  Pure driver-API code; no CPU evaluation path exists here.
+#include <algorithm>
 #include <atomic>
 #include <cerrno>
 #include <chrono>
@@ -141,7 +142,7 @@ struct DeviceState {
   CUcontext ctx = nullptr;
   CUstream compute = nullptr, copy = nullptr;
   CUevent ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
-  CUevent ev_t0 = nullptr, ev_t1 = nullptr;
+  CUevent ev_t0 = nullptr, ev_t1 = nullptr, ev_g0 = nullptr, ev_g1 = nullptr;
   std::mutex mu;  // one grid call at a time per device (scratch buffers are shared)
   DevBuf d_p, d_pc, d_rc, d_xs, d_out[2];
   PinBuf stage[2];
@@ -200,6 +201,8 @@ static inflx_status get_device(int ordinal, DeviceState** out) {
   }
   CU_TRY(cu.p_cuEventCreate(&d->ev_t0, CU_EVENT_DEFAULT));
   CU_TRY(cu.p_cuEventCreate(&d->ev_t1, CU_EVENT_DEFAULT));
+  CU_TRY(cu.p_cuEventCreate(&d->ev_g0, CU_EVENT_DEFAULT));
+  CU_TRY(cu.p_cuEventCreate(&d->ev_g1, CU_EVENT_DEFAULT));
   *out = d.get();
   g_devices[ordinal] = std::move(d);
   return INFLX_OK;
@@ -341,7 +344,7 @@ struct Shard {
 struct ShardResult {
   inflx_status status = INFLX_OK;
   std::string error;
-  double kernel_ms = 0;
+  double kernel_ms = 0, grid_ms = 0;
   uint64_t launches = 0, d2h = 0, h2d = 0;
 };
 
@@ -521,11 +524,13 @@ static inflx_status run_shard(inflx_lib* lib, const inflx_grid_request& rq, cons
         outp = dev->d_out[slot].ptr;
       }
       double aux = rq.aux;
+      if (k == 0) CU_TRY(cu.p_cuEventRecord(dev->ev_g0, cs));
       void* args[] = {&outp, &dev->d_rc.ptr, &of1, &dx1, &n1u, &n_rows, &comp_stride, &aux};
       if ((st = launch(cu, grid_fn, (unsigned)((n1 + BLOCK - 1) / BLOCK),
                        (unsigned)((rc + RPT - 1) / RPT), (unsigned)sc, BLOCK, cs, args)))
         return st;
       res.launches++;
+      if (to_device) CU_TRY(cu.p_cuEventRecord(dev->ev_g1, cs));
       if (!to_device) {
         CU_TRY(cu.p_cuEventRecord(dev->ev_done[slot], cs));
         CU_TRY(cu.p_cuStreamWaitEvent(dev->copy, dev->ev_done[slot], 0));
@@ -549,6 +554,10 @@ static inflx_status run_shard(inflx_lib* lib, const inflx_grid_request& rq, cons
     float ms = 0;
     CU_TRY(cu.p_cuEventElapsedTime(&ms, dev->ev_t0, dev->ev_t1));
     res.kernel_ms = ms;
+    if (to_device) {
+      CU_TRY(cu.p_cuEventElapsedTime(&ms, dev->ev_g0, dev->ev_g1));
+      res.grid_ms = ms;
+    }
   }
   return INFLX_OK;
 }
@@ -759,6 +768,7 @@ inflx_status inflx_grid_eval(inflx_lib* lib, const inflx_grid_request* rq,
   for (auto& r : results) {
     if (r.status) return fail(r.status, r.error);
     rep.kernel_ms = std::max(rep.kernel_ms, r.kernel_ms);
+    rep.grid_ms = std::max(rep.grid_ms, r.grid_ms);
     rep.launches += r.launches;
     rep.d2h_bytes += r.d2h;
     rep.h2d_bytes += r.h2d;
@@ -1126,6 +1136,68 @@ inflx_status inflx_validate_basis_on_domain(inflx_lib* lib, const uint32_t* num_
              "This could be indicative of a defective model.\nUsed parameter values: p=%s", failed,
              (double)num_points[0] * (double)num_points[1], params_dbg(pv).c_str()));
   }
+  return INFLX_OK;
+}
+
+// ---- roofline denominator: sustained FP64 FMA rate of one device -------------------------------
+// MEASURED_PEAKS.json carries no fp64 entry, so the bench measures it with this micro-kernel:
+// 8 independent DFMA chains per thread, enough resident warps to saturate the FP64 pipe.
+static const char* kPeakSrc = R"(
+extern "C" __global__ void inflx_dfma_peak(double* out, double a, double b, int iters) {
+  double x0 = threadIdx.x * 1e-9, x1 = x0 + 1., x2 = x0 + 2., x3 = x0 + 3., x4 = x0 + 4.,
+         x5 = x0 + 5., x6 = x0 + 6., x7 = x0 + 7.;
+#pragma unroll 4
+  for (int i = 0; i < iters; ++i) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+  if (s == 123.456) out[0] = s;
+}
+)";
+
+inflx_status inflx_measure_fp64_peak(int device, int repeats, double* tflops_best,
+                                     double* tflops_median) {
+  CudaDriver& cu = CudaDriver::get();
+  DeviceState* dev = nullptr;
+  inflx_status st = get_device(device, &dev);
+  if (st) return st;
+  void* cubin = nullptr;
+  size_t size = 0;
+  char* log = nullptr;
+  const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17"};
+  st = inflx_nvrtc_compile(kPeakSrc, "inflx_peak.cu", opts, 2, &cubin, &size, &log);
+  free(log);
+  if (st) return st;
+  std::lock_guard<std::mutex> lk(dev->mu);
+  CU_TRY(cu.p_cuCtxSetCurrent(dev->ctx));
+  CUmodule mod = nullptr;
+  CUresult r = cu.p_cuModuleLoadData(&mod, cubin);
+  free(cubin);
+  if (r != CUDA_SUCCESS) return fail(INFLX_ERR_CUDA, "cuModuleLoadData(peak kernel) failed");
+  CUfunction fn = nullptr;
+  CU_TRY(cu.p_cuModuleGetFunction(&fn, mod, "inflx_dfma_peak"));
+  if ((st = ensure_dev(cu, dev->d_p, 64))) return st;
+  int sms = 0;
+  cu.p_cuDeviceGetAttribute(&sms, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, dev->dev);
+  const unsigned blocks = (unsigned)sms * 8, threads = 256;
+  int iters = 1 << 15;
+  double a = 1.0000001, b = 1e-9;
+  void* args[] = {&dev->d_p.ptr, &a, &b, &iters};
+  std::vector<double> tf;
+  for (int k = 0; k < repeats + 2; ++k) {
+    CU_TRY(cu.p_cuEventRecord(dev->ev_t0, dev->compute));
+    if ((st = launch(cu, fn, blocks, 1, 1, threads, dev->compute, args))) return st;
+    CU_TRY(cu.p_cuEventRecord(dev->ev_t1, dev->compute));
+    CU_TRY(cu.p_cuStreamSynchronize(dev->compute));
+    float ms = 0;
+    CU_TRY(cu.p_cuEventElapsedTime(&ms, dev->ev_t0, dev->ev_t1));
+    if (k >= 2) tf.push_back(2.0 * 8 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12);
+  }
+  cu.p_cuModuleUnload(mod);
+  std::sort(tf.begin(), tf.end());
+  *tflops_best = tf.back();
+  *tflops_median = tf[tf.size() / 2];
   return INFLX_OK;
 }
 

@@ -380,7 +380,7 @@ def grid_eval(lib, op: str, p, out, n0: int, n1: int, start_stop, rows=None, acc
         _native.lib().inflx_grid_eval(lib._h, ctypes.byref(rq), ctypes.byref(rep))
     )
     return {
-        "kernel_ms": rep.kernel_ms, "total_ms": rep.total_ms, "launches": int(rep.launches),
+        "kernel_ms": rep.kernel_ms, "grid_ms": rep.grid_ms, "total_ms": rep.total_ms, "launches": int(rep.launches),
         "d2h_bytes": int(rep.d2h_bytes), "h2d_bytes": int(rep.h2d_bytes),
         "n_devices": rep.n_devices,
     }  # fmt: skip
