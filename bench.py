@@ -247,12 +247,10 @@ def main():
     ss = np.array(ext, dtype=np.float64)
 
     # shard: rows when a single vector, vectors for the sweep
-    if S == 1:
-        r0, r1 = n0 * rank // world, n0 * (rank + 1) // world
-        p_local = p
-    else:
-        r0, r1 = 0, n0
-        p_local = np.ascontiguousarray(p[S * rank // world : S * (rank + 1) // world])
+    from inflatox_b200.sharding import shard
+
+    (r0, r1), (s0, s1) = shard(n0, S, rank, world)
+    p_local = np.ascontiguousarray(p[s0:s1])
     S_local = p_local.shape[0]
     my_points = S_local * (r1 - r0) * n1
     total_points = S * n0 * n1

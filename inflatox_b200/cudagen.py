@@ -120,7 +120,14 @@ class ModelRoots:
 
 
 class GroupProgram:
-    """Classification, frontiers, flop counts and CUDA text for one group of model functions."""
+    """Classification, frontiers, flop counts and CUDA text for one group of model functions.
+
+    Works on a *local* node table: the DAG nodes reachable from the group's roots plus one
+    pseudo-node ("rcp", b) per distinct denominator b of a division.  ("rcp", b) stands for the
+    refined reciprocal `inflx_rcp_s(b)` the speculative division needs; being a node, it is
+    classified and hoisted like any other value, so a per-point quotient by a row- or
+    parameter-class denominator costs 3 FP64 instructions instead of 9.
+    """
 
     def __init__(self, dag: Dag, roots: ModelRoots, group: str, n_params: int):
         self.dag = dag
@@ -129,17 +136,55 @@ class GroupProgram:
         grid_names, point_names, self.grid_ops, self.point_ops = GROUPS[group]
         self.grid_roots = {n: roots.node[n] for n in grid_names}
         self.point_roots = {n: roots.node[n] for n in grid_names + point_names}
-        self.all_nodes = dag.reachable(self.point_roots.values())
-        self.grid_nodes = dag.reachable(self.grid_roots.values())
+        self.extra: dict[int, tuple] = {}  # pseudo-nodes, ids >= len(dag.nodes)
+        self.rcp_of: dict[int, int] = {}  # denominator node -> its ("rcp", b) pseudo-node
+        self.all_nodes = self._with_reciprocals(dag.reachable(self.point_roots.values()))
+        grid_plain = set(dag.reachable(self.grid_roots.values()))
+        self.grid_nodes = [
+            i
+            for i in self.all_nodes
+            if i in grid_plain or (i in self.extra and self._rcp_used_by_grid(i, grid_plain))
+        ]
         self._classify()
         self._frontiers()
 
+    # -- local node table ----------------------------------------------------------------------
+    def node(self, i: int) -> tuple:
+        return self.extra[i] if i in self.extra else self.dag.nodes[i]
+
+    def operands(self, i: int) -> tuple[int, ...]:
+        n = self.node(i)
+        if n[0] == "rcp":
+            return (n[1],)
+        ops = self.dag.operands(i)
+        if n[0] == "/" and n[2] in self.rcp_of:
+            return ops + (self.rcp_of[n[2]],)
+        return ops
+
+    def _with_reciprocals(self, nodes: list[int]) -> list[int]:
+        out = []
+        next_id = len(self.dag.nodes)
+        for i in nodes:
+            n = self.dag.nodes[i]
+            if n[0] == "/" and n[2] not in self.rcp_of:
+                self.extra[next_id] = ("rcp", n[2])
+                self.rcp_of[n[2]] = next_id
+                out.append(next_id)  # topological: right before its first user
+                next_id += 1
+            out.append(i)
+        return out
+
+    def _rcp_used_by_grid(self, r: int, grid_plain: set) -> bool:
+        b = self.extra[r][1]
+        return any(
+            self.dag.nodes[i][0] == "/" and self.dag.nodes[i][2] == b for i in grid_plain
+        )
+
     # -- analysis ----------------------------------------------------------------------------
     def _classify(self):
-        d = self.dag
         dep: dict[int, int] = {}
         for i in self.all_nodes:
-            n = d.nodes[i]
+            n = self.node(i)
             k = n[0]
             if k == "x":
                 if n[1] > 1:
@@ -155,7 +200,7 @@ class GroupProgram:
                 raise Exception("field velocities are not part of the grid-evaluation path")
             else:
                 b = 0
-                for o in d.operands(i):
+                for o in self.operands(i):
                     b |= dep[o]
                 dep[i] = b
         self.dep = dep
@@ -176,11 +221,11 @@ class GroupProgram:
         return "M"
 
     def _frontiers(self):
-        d = self.dag
         users: dict[int, list[int]] = {}
         for i in self.all_nodes:
-            for o in d.operands(i):
+            for o in self.operands(i):
                 users.setdefault(o, []).append(i)
+        self.users = users
         root_ids = set(self.point_roots.values())
         self.p_frontier = [
             i
@@ -203,18 +248,19 @@ class GroupProgram:
         self.r_slot = {n: k for k, n in enumerate(self.r_frontier)}
 
     def is_op(self, i: int) -> bool:
-        return self.dag.nodes[i][0] in ("+", "-", "*", "/", "neg", "f")
+        return self.node(i)[0] in ("+", "-", "*", "/", "neg", "f", "rcp")
 
     def nodes_of(self, classes: str, within=None) -> list[int]:
         src = self.all_nodes if within is None else within
         return [i for i in src if self.is_op(i) and self.klass(i) in classes]
 
     def flops(self, nodes) -> int:
-        """Algorithmic flops of `nodes` by the SURVEY.md 8(d) rule."""
+        """Algorithmic flops of `nodes` by the SURVEY.md 8(d) rule (reciprocal pseudo-nodes are
+        an implementation detail of the division and count as nothing)."""
         d = self.dag
         total = 0
         for i in nodes:
-            n = d.nodes[i]
+            n = self.node(i)
             k = n[0]
             if k in ("+", "-", "*", "/"):
                 total += 1
@@ -232,11 +278,14 @@ class GroupProgram:
         g = self.grid_nodes
         ops = [i for i in g if self.is_op(i)]
         cnt = {c: len([i for i in ops if self.klass(i) == c]) for c in "PRCM"}
+        per_point = [i for i in ops if self.klass(i) == "M"]
         return {
-            "dag_ops": len(ops),
+            "dag_ops": len([i for i in ops if self.node(i)[0] != "rcp"]),
             "class_ops": cnt,
             "flops_model": self.flops(ops),
-            "flops_per_point_executed": self.flops([i for i in ops if self.klass(i) == "M"]),
+            "flops_per_point_executed": self.flops(per_point),
+            "divisions_per_point": len([i for i in per_point if self.node(i)[0] == "/"]),
+            "reciprocals_per_point": len([i for i in per_point if self.node(i)[0] == "rcp"]),
             "n_p_frontier": len(self.p_frontier),
             "n_r_frontier": len(self.r_frontier),
         }
@@ -246,17 +295,25 @@ class GroupProgram:
         """C expression naming node `i` inside a kernel whose already-bound values are `scope`."""
         if i in scope:
             return scope[i]
-        n = self.dag.nodes[i]
+        n = self.node(i)
         if n[0] == "c":
             return _lit(n[1])
         if n[0] == "i":
             return _lit(float(n[1]))
         raise KeyError(f"node {i} {n} is not available in this scope")
 
-    def _expr(self, i: int, scope: dict[int, str]) -> str:
+    def _expr(self, i: int, scope: dict[int, str], spec: bool) -> str:
+        """`spec`: branch-free speculative division / sqrt (per-point code of the grid kernels);
+        otherwise the compiler's IEEE operators."""
         d = self.dag
-        n = d.nodes[i]
+        n = self.node(i)
         k = n[0]
+        pol = "inflx_spec(bad)" if spec else "inflx_exact()"
+        if k == "rcp":
+            return f"inflx_rcp_s({self._ref(n[1], scope)})"
+        if k == "/" and spec:
+            y = self._ref(self.rcp_of[n[2]], scope)
+            return f"inflx_div_y({self._ref(n[1], scope)}, {self._ref(n[2], scope)}, {y}, bad)"
         if k in ("+", "-", "*", "/"):
             return f"{self._ref(n[1], scope)} {k} {self._ref(n[2], scope)}"
         if k == "neg":
@@ -268,23 +325,36 @@ class GroupProgram:
                 e = float(d.cval(n[3]))
                 if e.is_integer() and 1 <= abs(e) <= MAX_FAST_POW:
                     e = int(e)
-                    fn = f"inflx_powi<{e}>" if e > 0 else f"inflx_powi_neg<{-e}>"
-                    return f"{fn}({args[0]})"
+                    if e > 0:
+                        return f"inflx_powi<{e}>({args[0]})"
+                    return f"inflx_powi_neg<{-e}>({args[0]}, {pol})"
                 e2 = 2.0 * e
                 if e2.is_integer() and abs(e2) <= 2 * MAX_FAST_POW:
                     e2 = int(e2)  # odd
-                    fn = f"inflx_powh<{(e2 - 1) // 2}>" if e2 > 0 else f"inflx_powh_neg<{(-e2 - 1) // 2}>"
-                    return f"{fn}({args[0]})"
+                    if e2 > 0:
+                        return f"inflx_powh<{(e2 - 1) // 2}>({args[0]}, {pol})"
+                    return f"inflx_powh_neg<{(-e2 - 1) // 2}>({args[0]}, {pol})"
+            if name == "sqrt" and spec:
+                return f"inflx_sqrt_s({args[0]}, bad)"
             return f"{name}({', '.join(args)})"
         raise KeyError(f"cannot emit node {i}: {n}")
 
-    def _block(self, nodes: list[int], scope: dict[int, str], indent: str) -> str:
-        """SSA statements for `nodes` (topological order); extends `scope` with their names."""
+    def _block(self, nodes, scope, indent: str, spec: bool = False, lazy=None) -> str:
+        """SSA statements for `nodes` (topological order); extends `scope` with their names.
+        `lazy` maps not-yet-loaded nodes to their load expression: the load is emitted right
+        before the first statement that uses the value (keeps live ranges short)."""
         out = []
         for i in nodes:
             if i in scope:
                 continue
-            out.append(f"{indent}const double t{i} = {self._expr(i, scope)};")
+            if self.node(i)[0] == "rcp" and not spec:
+                continue  # exact code divides with the IEEE operator and needs no reciprocal
+            if lazy:
+                for o in self.operands(i):
+                    if o in lazy and o not in scope:
+                        out.append(f"{indent}const double r{o} = {lazy[o]};")
+                        scope[o] = f"r{o}"
+            out.append(f"{indent}const double t{i} = {self._expr(i, scope, spec)};")
             scope[i] = f"t{i}"
         return "\n".join(out) + ("\n" if out else "")
 
@@ -292,8 +362,8 @@ class GroupProgram:
         """Names for leaves; `extra` maps ('x',0) etc. to C identifiers."""
         scope = {}
         for i in self.all_nodes:
-            n = self.dag.nodes[i]
-            if (n[0], n[1]) in extra and n[0] in ("x", "p", "v1", "v2"):
+            n = self.node(i)
+            if n[0] in ("x", "p", "v1", "v2") and (n[0], n[1]) in extra:
                 scope[i] = extra[(n[0], n[1])]
         return scope
 
@@ -309,7 +379,13 @@ class GroupProgram:
 
         # ---- (1) parameter block: one thread per parameter vector ----
         scope = self._leaf_scope({("p", k): f"p[{k}]" for k in range(self.n_params)})
-        body = self._block(self.nodes_of("P"), scope, "  ")
+        body = self._block(self.nodes_of("P"), scope, "  ", spec=False)
+        # reciprocals of P-class denominators are skipped by the exact block; emit the ones the
+        # faster classes read
+        for n in self.p_slot:
+            if n not in scope and self.node(n)[0] == "rcp":
+                body += f"  const double t{n} = {self._expr(n, scope, False)};\n"
+                scope[n] = f"t{n}"
         stores = "".join(
             f"  pc[{k}] = {self._ref(n, scope)};\n" for n, k in self.p_slot.items()
         )
@@ -323,13 +399,14 @@ class GroupProgram:
             "  (void)p; (void)pc;\n" + body + stores + "}\n\n"
         )
 
-        def pc_scope(sweep_expr: str) -> dict[int, str]:
-            return {n: f"inflx_pc[{sweep_expr}{k}]" for n, k in self.p_slot.items()}
-
         # ---- (2) row block: one thread per (row, parameter vector) ----
-        scope = pc_scope("pbase + ")
+        scope = {n: f"inflx_pc[pbase + {k}]" for n, k in self.p_slot.items()}
         scope.update(self._leaf_scope({("x", 0): "x0"}))
-        body = self._block(self.nodes_of("R", self.grid_nodes), scope, "  ")
+        body = self._block(self.nodes_of("R", self.grid_nodes), scope, "  ", spec=False)
+        for n in self.r_slot:
+            if n not in scope and self.node(n)[0] == "rcp":
+                body += f"  const double t{n} = {self._expr(n, scope, False)};\n"
+                scope[n] = f"t{n}"
         stores = "".join(
             f"  rr[{k}] = {self._ref(n, scope)};\n" for n, k in self.r_slot.items()
         )
@@ -344,7 +421,8 @@ class GroupProgram:
             "  (void)pbase; (void)x0; (void)rr;\n" + body + stores + "}\n\n"
         )
 
-        # ---- (3) grid kernels: thread = column, walks INFLX_RPT rows ----
+        # ---- (3) slow path + grid kernels: thread = column, walks INFLX_RPT rows ----
+        src.append(self._slow_function())
         for op in self.grid_ops:
             for sweep in (False, True):
                 src.append(self._grid_kernel(op, sweep))
@@ -353,68 +431,110 @@ class GroupProgram:
             src.append(self._point_kernel(op))
         return "".join(src)
 
-    def _epilogue(self, op: str, val, point: str, indent: str) -> str:
+    def _epilogue(self, op: str, val, point: str, indent: str, spec: bool) -> str:
         """Statement(s) writing the result of `op` for the point with flat index `point`."""
+        s, b = ("_s", ", bad") if spec else ("", "")
         if op == "complete_analysis":
             return (
-                f"{indent}inflx_store6(out, {point}, inflx_op_complete({val('V')}, {val('v00')}, "
-                f"{val('v10')}, {val('v11')}, {val('g2')}));\n"
+                f"{indent}o6 = inflx_op_complete{s}({val('V')}, {val('v00')}, "
+                f"{val('v10')}, {val('v11')}, {val('g2')}{b});\n"
             )
         if op == "consistency_only":
             return (
-                f"{indent}out[{point}] = inflx_op_consistency({val('V')}, {val('v00')}, "
-                f"{val('v10')}, {val('v11')});\n"
+                f"{indent}o1 = inflx_op_consistency{s}({val('V')}, {val('v00')}, "
+                f"{val('v10')}, {val('v11')}{b});\n"
             )
         if op == "consistency_rapidturn_only":
             return (
-                f"{indent}out[{point}] = inflx_op_rapidturn({val('V')}, {val('v00')}, "
-                f"{val('v10')}, {val('v11')});\n"
+                f"{indent}o1 = inflx_op_rapidturn{s}({val('V')}, {val('v00')}, "
+                f"{val('v10')}, {val('v11')}{b});\n"
             )
         if op == "epsilon_v_only":
-            return f"{indent}out[{point}] = inflx_op_epsilon_v({val('V')}, {val('g2')});\n"
+            return f"{indent}o1 = inflx_op_epsilon_v{s}({val('V')}, {val('g2')}{b});\n"
         if op == "flag_quantum_dif":
-            return (
-                f"{indent}reinterpret_cast<unsigned char*>(out)[{point}] = "
-                f"inflx_op_flag({val('b0')}, {val('b1')}, aux);\n"
-            )
+            return f"{indent}o1 = (double)inflx_op_flag({val('b0')}, {val('b1')}, aux);\n"
         if op == "potential":
-            return f"{indent}out[{point}] = {val('V')};\n"
+            return f"{indent}o1 = {val('V')};\n"
+        if op == "hesse":
+            return "".join(
+                f"{indent}o4[{c}] = {val(nm)};\n"
+                for c, nm in enumerate(("v00", "v01", "v10", "v11"))
+            )
         raise KeyError(op)
+
+    def _store(self, op: str, point: str, indent: str) -> str:
+        if op == "complete_analysis":
+            return f"{indent}inflx_store6(out, {point}, o6);\n"
+        if op == "flag_quantum_dif":
+            return f"{indent}reinterpret_cast<unsigned char*>(out)[{point}] = (unsigned char)(o1 != 0.0);\n"
+        if op == "hesse":
+            # (2,2,N0,N1) component-major output (reference src/hesse_bindings.rs:150-192)
+            return "".join(
+                f"{indent}out[{c}ull * comp_stride + {point}] = o4[{c}];\n" for c in range(4)
+            )
+        return f"{indent}out[{point}] = o1;\n"
+
+    def _root_order(self) -> list[str]:
+        return list(self.grid_roots)
+
+    def _slow_function(self) -> str:
+        """Exact (IEEE-operator) recomputation of the group's root values at one grid point; run
+        only for points whose speculative division / sqrt left the validated range."""
+        scope = {n: f"inflx_pc[pbase + {k}]" for n, k in self.p_slot.items()}
+        scope.update(self._leaf_scope({("x", 1): "x1"}))
+        lazy = {n: f"__ldg(rr + {k})" for n, k in self.r_slot.items()}
+        body = self._block(self.nodes_of("CM", self.grid_nodes), scope, "  ", False, lazy)
+        outs = ""
+        for k, nm in enumerate(self._root_order()):
+            r = self.grid_roots[nm]
+            if r in lazy and r not in scope:
+                outs += f"  roots[{k}] = {lazy[r]};\n"
+            else:
+                outs += f"  roots[{k}] = {self._ref(r, scope)};\n"
+        return (
+            "__device__ __noinline__ void inflx_slow_roots(const double* __restrict__ rr, double x1, "
+            "u32 pbase, double* __restrict__ roots) {\n  (void)rr; (void)x1; (void)pbase;\n"
+            + body + outs + "}\n\n"
+        )
 
     def _grid_kernel(self, op: str, sweep: bool) -> str:
         name = f"inflx_grid_{op}" + ("_sweep" if sweep else "")
         pbase = "pbase + " if sweep else ""
         scope = {n: f"inflx_pc[{pbase}{k}]" for n, k in self.p_slot.items()}
         scope.update(self._leaf_scope({("x", 1): "x1"}))
-        col_block = self._block(self.nodes_of("C", self.grid_nodes), scope, "  ")
-        # row-frontier loads (warp-uniform addresses) + the per-point block
-        loads = "".join(
-            f"    const double r{n} = __ldg(rr + {k});\n" for n, k in self.r_slot.items()
-        )
-        for n in self.r_slot:
-            scope[n] = f"r{n}"
-        mixed = self._block(self.nodes_of("M", self.grid_nodes), scope, "    ")
+        col_block = self._block(self.nodes_of("C", self.grid_nodes), scope, "  ", spec=True)
+        col_block = col_block.replace(", bad)", ", bad_c)").replace("(bad)", "(bad_c)")
+        lazy = {n: f"__ldg(rr + {k})" for n, k in self.r_slot.items()}
+        mixed = self._block(self.nodes_of("M", self.grid_nodes), scope, "    ", True, lazy)
+        root_loads = ""
+        for nm, r in self.grid_roots.items():  # roots that are plain row-frontier values
+            if r in lazy and r not in scope:
+                root_loads += f"    const double r{r} = {lazy[r]};\n"
+                scope[r] = f"r{r}"
 
         def val(rname: str) -> str:
             return self._ref(self.grid_roots[rname], scope)
 
-        if op == "hesse":
-            # (2,2,N0,N1) component-major output (reference src/hesse_bindings.rs:150-192)
-            epi = "".join(
-                f"    out[{c}ull * comp_stride + point] = {val(nm)};\n"
-                for c, nm in enumerate(("v00", "v01", "v10", "v11"))
-            )
-        else:
-            epi = self._epilogue(op, val, "point", "    ")
+        order = self._root_order()
+
+        def slow_val(rname: str) -> str:
+            return f"roots[{order.index(rname)}]"
+
+        decl = {"complete_analysis": "inflx_six o6;", "hesse": "double o4[4];"}.get(op, "double o1;")
         return (
-            f"extern \"C\" __global__ void __launch_bounds__(INFLX_BLOCK) {name}("
+            f"extern \"C\" __global__ void __launch_bounds__(INFLX_BLOCK, INFLX_MIN_BLOCKS) {name}("
             "double* __restrict__ out, const double* __restrict__ rc, double of1, double dx1, "
             "u32 n1, u32 n_rows, u64 comp_stride, double aux) {\n"
             "  const u32 col = blockIdx.x * INFLX_BLOCK + threadIdx.x;\n"
             "  if (col >= n1) return;\n"
-            + ("  const u32 s = blockIdx.z;\n  const u32 pbase = s * INFLX_NPF;\n" if sweep else "  const u32 s = 0;\n")
+            + (
+                "  const u32 s = blockIdx.z;\n  const u32 pbase = s * INFLX_NPF;\n"
+                if sweep
+                else "  const u32 s = 0;\n  const u32 pbase = 0;\n"
+            )
             + "  const double x1 = inflx_coord(col, dx1, of1);\n"
-            "  (void)x1; (void)aux; (void)comp_stride; (void)rc;\n"
+            "  bool bad_c = false;\n"
+            "  (void)x1; (void)aux; (void)comp_stride; (void)rc; (void)pbase;\n"
             + col_block
             + "  const u32 r0 = blockIdx.y * INFLX_RPT;\n"
             "#pragma unroll 1\n"
@@ -424,7 +544,19 @@ class GroupProgram:
             "    const u64 rowid = (u64)s * n_rows + i;\n"
             "    const double* __restrict__ rr = rc + rowid * INFLX_NRF;\n"
             "    const u64 point = rowid * n1 + col;\n"
-            "    (void)rr;\n" + loads + mixed + epi + "  }\n}\n\n"
+            "    bool bad = bad_c;\n"
+            f"    {decl}\n"
+            "    (void)rr;\n"
+            + mixed
+            + root_loads
+            + self._epilogue(op, val, "point", "    ", True)
+            + "    if (bad) {  // rare: redo this point with the IEEE operators\n"
+            f"      double roots[{len(order)}];\n"
+            "      inflx_slow_roots(rr, x1, pbase, roots);\n"
+            + self._epilogue(op, slow_val, "point", "      ", False)
+            + "    }\n"
+            + self._store(op, "point", "    ")
+            + "  }\n}\n\n"
         )
 
     def _point_kernel(self, op: str) -> str:
@@ -435,17 +567,15 @@ class GroupProgram:
         roots = self.point_roots if op == "basis" else self.grid_roots
         want = [r for nm, r in roots.items() if nm != "ip"]
         nodes = [i for i in self.dag.reachable(want) if self.is_op(i) and self.klass(i) in "RCM"]
-        body = self._block(nodes, scope, "  ")
+        body = self._block(nodes, scope, "  ", spec=False)
 
         def val(rname: str) -> str:
             return self._ref(roots[rname], scope)
 
         pre = ""
         if op == "hesse":
-            epi = "".join(
-                f"  out[k * 4 + {c}] = {val(nm)};\n"
-                for c, nm in enumerate(("v00", "v01", "v10", "v11"))
-            )
+            epi = "  double o4[4];\n" + self._epilogue(op, val, "k", "  ", False)
+            epi += "".join(f"  out[k * 4 + {c}] = o4[{c}];\n" for c in range(4))
         elif op == "basis":
             # v, w1 and the three metric inner products (reference src/lib.rs:142-203)
             pre = self._inner_function()
@@ -457,7 +587,8 @@ class GroupProgram:
                 "  out[k * 7 + 6] = inflx_inner(x0, x1, w0, w1, w0, w1);\n"
             )
         else:
-            epi = self._epilogue(op, val, "k", "  ")
+            decl = "inflx_six o6;" if op == "complete_analysis" else "double o1;"
+            epi = f"  {decl}\n" + self._epilogue(op, val, "k", "  ", False) + self._store(op, "k", "  ")
         return (
             pre
             + f"extern \"C\" __global__ void inflx_points_{op}(double* __restrict__ out, "
@@ -482,7 +613,7 @@ class GroupProgram:
         nodes = [
             i for i in self.dag.reachable([root]) if self.is_op(i) and self.klass(i) in "RCMV"
         ]
-        body = self._block(nodes, scope, "  ")
+        body = self._block(nodes, scope, "  ", spec=False)
         return (
             "__device__ __noinline__ double inflx_inner(double x0, double x1, double a0, double a1, "
             "double c0, double c1) {\n  (void)x0; (void)x1; (void)a0; (void)a1; (void)c0; (void)c1;\n"

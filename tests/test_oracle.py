@@ -1,0 +1,89 @@
+"""The oracle pinned on every known answer the reference's own tests hold for the hot path
+(reference tests/test_doc.py:50, 51, 58) and on the reference's parameter order."""
+import math
+
+import numpy as np
+import pytest
+
+import cases
+import oracle
+
+
+@pytest.fixture(scope="module")
+def doc():
+    return oracle.Oracle("doc")
+
+
+def test_calc_V_known_answer(doc):
+    # reference tests/test_doc.py:50 - exact equality
+    assert doc.potential([2.0, -2.0], [1.0]) == 1.9166666666666667
+
+
+def test_calc_H_known_answer(doc):
+    # reference tests/test_doc.py:51
+    want = np.array([[0.41206897, -1.05517241], [-1.05517241, -0.07873563]])
+    assert np.allclose(doc.hesse([2.0, -2.0], [1.0]), want)
+
+
+def test_complete_analysis_consistency_bounded(doc):
+    # reference tests/test_doc.py:53-58: default 1000 x 1000 grid
+    out = doc.complete_analysis([1.0], 1000, 1000, (0.0, 2.5, 0.0, math.pi))
+    assert np.nanmax(out[..., 0]) <= 1.0
+
+
+def test_symbol_order_matches_reference_tests():
+    want = {
+        "hyper": ["m", "φ0", "L"],
+        "angular": ["alpha", "m_chi", "m_phi"],
+        "egno": ["m", "a", "c", "alpha"],
+        "d5": ["V0", "a0", "p", "q", "u", "l_s", "a1", "b1", "g_s", "N"],
+    }
+    for model, names in want.items():
+        d = oracle.golden_meta(model)["symbol_dictionary"]
+        got = sorted((v, k) for k, v in d.items() if v.startswith("args"))
+        got = [k for _, k in sorted(got, key=lambda t: int(t[0][5:-1]))]
+        assert got == names, (model, got)
+
+
+def test_grid_conventions():
+    """spacing = (stop-start)/N (endpoint excluded), axis 0 <-> x[0] <-> rows, AoS output."""
+    o = oracle.Oracle("doc")
+    n0, n1, ext = 7, 5, (0.5, 2.5, 0.25, 3.0)
+    grid = o.potential_array([1.0], n0, n1, ext)
+    for i in (0, 3, 6):
+        for j in (0, 2, 4):
+            x0 = i * ((ext[1] - ext[0]) / n0) + ext[0]
+            x1 = j * ((ext[3] - ext[2]) / n1) + ext[2]
+            assert grid[i, j] == o.potential([x0, x1], [1.0])
+    full = o.complete_analysis([1.0], n0, n1, ext)
+    part = o.complete_analysis([1.0], n0, n1, ext, rows=(2, 5))
+    assert np.array_equal(full[2:5], part, equal_nan=True)
+    # epsilon_v_only carries the factor 1/2 that complete_analysis' eps_V lacks (anguelova.rs:119,139)
+    ev = o.epsilon_v_only([1.0], n0, n1, ext)
+    assert np.allclose(ev, 0.5 * full[..., 1], rtol=1e-15, equal_nan=True)
+
+
+def test_hyperinflation_quirks():
+    """v10 == 0 for the README model: consistency plane all NaN, delta == 0."""
+    o = oracle.Oracle("hyper")
+    out = o.complete_analysis(cases.params("hyper"), 64, 64, cases.EXTENT["hyper"])
+    assert np.isnan(out[..., 0]).all()
+    assert (out[..., 4] == 0).all()
+
+
+def test_threads_do_not_change_results():
+    o = oracle.Oracle("angular")
+    p, ext = cases.params("angular"), cases.EXTENT["angular"]
+    a = o.complete_analysis(p, 96, 80, ext, threads=1)
+    b = o.complete_analysis(p, 96, 80, ext, threads=4)
+    assert np.array_equal(a, b, equal_nan=True)
+
+
+def test_quad_truth_brackets_the_double_oracle():
+    """The __float128 build of the same generated C agrees with the double oracle where the
+    model is well conditioned (doc model, eps_V plane)."""
+    p, ext = [1.0], (0.2, 2.5, 0.1, 3.0)
+    a = oracle.Oracle("doc").complete_analysis(p, 24, 24, ext)
+    q = oracle.Oracle("doc", quad=True).complete_analysis(p, 24, 24, ext)
+    err, fin, nan_mm, _ = cases.rel_err(a[..., 1], q[..., 1])
+    assert nan_mm == 0 and err[fin].max() < 1e-13
