@@ -246,6 +246,8 @@ class GroupProgram:
         ]
         self.p_slot = {n: k for k, n in enumerate(self.p_frontier)}
         self.r_slot = {n: k for k, n in enumerate(self.r_frontier)}
+        # rows of the row-frontier array are read with 128-bit loads: keep them 16-byte aligned
+        self.n_row_slots = (len(self.r_frontier) + 1) & ~1
 
     def is_op(self, i: int) -> bool:
         return self.node(i)[0] in ("+", "-", "*", "/", "neg", "f", "rcp")
@@ -288,6 +290,7 @@ class GroupProgram:
             "reciprocals_per_point": len([i for i in per_point if self.node(i)[0] == "rcp"]),
             "n_p_frontier": len(self.p_frontier),
             "n_r_frontier": len(self.r_frontier),
+            "n_row_slots": self.n_row_slots,
         }
 
     # -- emission ----------------------------------------------------------------------------
@@ -352,11 +355,23 @@ class GroupProgram:
             if lazy:
                 for o in self.operands(i):
                     if o in lazy and o not in scope:
-                        out.append(f"{indent}const double r{o} = {lazy[o]};")
-                        scope[o] = f"r{o}"
+                        out.append(self._load(o, lazy, scope, indent))
             out.append(f"{indent}const double t{i} = {self._expr(i, scope, spec)};")
             scope[i] = f"t{i}"
         return "\n".join(out) + ("\n" if out else "")
+
+    def _load(self, node: int, lazy: dict, scope: dict, indent: str) -> str:
+        """Row-frontier values travel in pairs: one 128-bit warp-uniform load brings slot 2k and
+        2k+1; the partner is bound too, so its own first use costs nothing."""
+        slot = self.r_slot[node]
+        pair = slot // 2
+        names = {k: n for n, k in self.r_slot.items()}
+        text = f"{indent}const double2 rp{pair} = __ldg(reinterpret_cast<const double2*>(rr) + {pair});\n"
+        for half, member in ((2 * pair, "x"), (2 * pair + 1, "y")):
+            n = names.get(half)
+            if n is not None and n not in scope:
+                scope[n] = f"rp{pair}.{member}"
+        return text.rstrip("\n")
 
     def _leaf_scope(self, extra: dict[tuple, str]) -> dict[int, str]:
         """Names for leaves; `extra` maps ('x',0) etc. to C identifiers."""
@@ -370,7 +385,7 @@ class GroupProgram:
     def cuda_source(self, model_name: str) -> str:
         with open(os.path.join(_CSRC, "inflx_device.cuh")) as fh:
             device_header = fh.read()
-        npf, nrf = len(self.p_frontier), len(self.r_frontier)
+        npf, nrf = len(self.p_frontier), self.n_row_slots
         src = [device_header]
         src.append(f'\n// ===== generated: model "{model_name}", group "{self.group}" =====\n')
         src.append(f"#define INFLX_NP {self.n_params}\n#define INFLX_NPF {npf}\n")
@@ -488,9 +503,8 @@ class GroupProgram:
         for k, nm in enumerate(self._root_order()):
             r = self.grid_roots[nm]
             if r in lazy and r not in scope:
-                outs += f"  roots[{k}] = {lazy[r]};\n"
-            else:
-                outs += f"  roots[{k}] = {self._ref(r, scope)};\n"
+                outs += self._load(r, lazy, scope, "  ") + "\n"
+            outs += f"  roots[{k}] = {self._ref(r, scope)};\n"
         return (
             "__device__ __noinline__ void inflx_slow_roots(const double* __restrict__ rr, double x1, "
             "u32 pbase, double* __restrict__ roots) {\n  (void)rr; (void)x1; (void)pbase;\n"
@@ -509,8 +523,7 @@ class GroupProgram:
         root_loads = ""
         for nm, r in self.grid_roots.items():  # roots that are plain row-frontier values
             if r in lazy and r not in scope:
-                root_loads += f"    const double r{r} = {lazy[r]};\n"
-                scope[r] = f"r{r}"
+                root_loads += self._load(r, lazy, scope, "    ") + "\n"
 
         def val(rname: str) -> str:
             return self._ref(self.grid_roots[rname], scope)
@@ -521,6 +534,9 @@ class GroupProgram:
             return f"roots[{order.index(rname)}]"
 
         decl = {"complete_analysis": "inflx_six o6;", "hesse": "double o4[4];"}.get(op, "double o1;")
+        # a root that is a compile-time constant (hyperinflation: v10 == 0) would send EVERY point
+        # of the speculative epilogue to the slow path (x/0); use the IEEE epilogue directly then
+        spec_epi = not any(self.klass(r) == "K" for r in self.grid_roots.values())
         return (
             f"extern \"C\" __global__ void __launch_bounds__(INFLX_BLOCK, INFLX_MIN_BLOCKS) {name}("
             "double* __restrict__ out, const double* __restrict__ rc, double of1, double dx1, "
@@ -549,7 +565,7 @@ class GroupProgram:
             "    (void)rr;\n"
             + mixed
             + root_loads
-            + self._epilogue(op, val, "point", "    ", True)
+            + self._epilogue(op, val, "point", "    ", spec_epi)
             + "    if (bad) {  // rare: redo this point with the IEEE operators\n"
             f"      double roots[{len(order)}];\n"
             "      inflx_slow_roots(rr, x1, pbase, roots);\n"
