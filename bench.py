@@ -138,6 +138,7 @@ def cpu_rate(model, op, n0, n1, ext, p, seconds, threads=0):
 
     orc = oracle.Oracle(model)
     fn = getattr(orc, op)
+    threads = threads or (os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1: be explicit
     probe_rows = max(1, min(n0, (1 << 20) // n1))
     t0 = time.perf_counter()
     fn(p, n0, n1, ext, rows=(0, probe_rows), threads=threads)
@@ -304,6 +305,8 @@ def main():
     if os.path.exists(tpath):
         with open(tpath) as fh:
             traffic = json.load(fh).get(f"{a.config}")
+        if traffic is not None:  # captured at N=1: per-launch traffic scales with the shard
+            traffic = traffic * my_points / total_points
     roofline = {
         "bound": "fp64", "kernel": f"inflx_grid_{op}", "achieved": achieved_tf, "peak": fp64_peak,
         "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak, "traffic": traffic,
@@ -336,13 +339,18 @@ def main():
                 return (time.perf_counter() - t0) * 1e3
             rep = rs.grid_eval(lib, op, p_local, h_out.reshape(-1), n0, n1, ss, rows=(r0, r1),
                                device=local)  # fmt: skip
+            if os.environ.get("INFLATOX_BENCH_VERBOSE"):
+                print(f"[rank {rank}] {rep}", file=sys.stderr)
             return rep["total_ms"]
 
         for _ in range(max(1, min(a.warmup, 2))):
             step_host()
         barrier()
-        e_ms = sum(step_host() for _ in range(a.steps))
+        per_step = [step_host() for _ in range(a.steps)]
+        e_ms = sum(per_step)
         barrier()
+        if os.environ.get("INFLATOX_BENCH_VERBOSE"):
+            print(f"[rank {rank}] e2e ms per step: {[round(t, 1) for t in per_step]}", file=sys.stderr)
         e_ms = max_over_ranks(e_ms)
         e2e = {
             "value": total_points * a.steps / (e_ms / 1e3), "unit": "points/s",

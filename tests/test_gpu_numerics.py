@@ -34,6 +34,14 @@ extern "C" __global__ void t_pow(const double* a, double* p3, double* p4, double
   ph[i] = inflx_powh<1>(x, inflx_exact());
   pmh[i] = inflx_powh_neg<0>(x, inflx_exact());
 }
+extern "C" __global__ void t_atan_tan(const double* y, const double* yinv, double* d, double* t,
+                                      double* d_ref, double* t_ref, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  inflx_atan_tan(y[i], yinv[i], d[i], t[i], inflx_exact());
+  d_ref[i] = atan(y[i]);       // libdevice, for comparison
+  t_ref[i] = tan(d_ref[i]);
+}
 """
 
 
@@ -120,3 +128,46 @@ def test_double_double_powers_are_correctly_rounded(mod):
             x = mpmath.mpf(float(a[k]))
             assert ph[k] == float(x * mpmath.sqrt(x))
             assert pmh[k] == float(1 / mpmath.sqrt(x))
+
+
+def test_atan_tan_helper_accuracy(mod):
+    """delta = atan(y) within 1 ulp; T within 3 ulp of tan(delta) for the delta actually returned
+    (200-bit mpmath references), over 600 decades of y and with the 1/y input off by up to 1 ulp
+    the way the epilogue's own quotient is."""
+    import mpmath
+
+    rng = np.random.default_rng(4)
+    n = 6000
+    y = 10.0 ** rng.uniform(-30, 30, n)
+    y[:2000] = 10.0 ** rng.uniform(-2, 2, 2000)
+    y[2000:2200] = 10.0 ** rng.uniform(14, 18, 200)  # delta rounds to within a few ulp of pi/2
+    y[-6:] = [0.0, 1.0, np.inf, 1.0000000000000002, 0.9999999999999999, 1e300]
+    yinv = 1.0 / y
+    yinv = np.where(rng.random(n) < 0.5, np.nextafter(yinv, np.inf), yinv)
+    yinv = np.where(rng.random(n) < 0.3, np.nextafter(yinv, 0), yinv)
+    yinv[~np.isfinite(1.0 / y)] = 0.0
+    yinv[y == 0] = np.inf
+    outs = [np.zeros(n) for _ in range(4)]
+    mod.launch("t_atan_tan", n, [np.ascontiguousarray(y), np.ascontiguousarray(yinv)], outs)
+    d, t, d_ref, t_ref = outs
+    worst_d = worst_t = worst_d_lib = worst_t_lib = 0.0
+    with mpmath.workprec(250):
+        for k in range(n):
+            yy = mpmath.mpf(float(y[k])) if np.isfinite(y[k]) else mpmath.inf
+            true_d = mpmath.atan(yy)
+            ulp_d = np.spacing(float(true_d))
+            worst_d = max(worst_d, abs(float((mpmath.mpf(float(d[k])) - true_d) / ulp_d)))
+            worst_d_lib = max(worst_d_lib, abs(float((mpmath.mpf(float(d_ref[k])) - true_d) / ulp_d)))
+            for dd, tt, which in ((d[k], t[k], 0), (d_ref[k], t_ref[k], 1)):
+                true_t = mpmath.tan(mpmath.mpf(float(dd)))
+                e = abs(float((mpmath.mpf(float(tt)) - true_t) / np.spacing(abs(float(true_t)) or 5e-324)))
+                if which == 0:
+                    worst_t = max(worst_t, e)
+                else:
+                    worst_t_lib = max(worst_t_lib, e)
+    print(f"atan: ours {worst_d:.2f} ulp, libdevice {worst_d_lib:.2f} ulp; "
+          f"tan(delta): ours {worst_t:.2f} ulp, libdevice {worst_t_lib:.2f} ulp")
+    assert worst_d <= 1.0, worst_d
+    assert worst_t <= 3.0, worst_t
+    assert d[-6] == 0.0 and t[-6] == 0.0  # y = 0
+    assert d[-4] == 1.5707963267948966 and abs(t[-4] / 1.633123935319537e16 - 1) < 1e-15  # y = inf
