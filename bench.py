@@ -151,7 +151,7 @@ def cpu_rate(model, op, n0, n1, ext, p, seconds, threads=0):
     return rows * n1 / dt, rows, r0, dt
 
 
-def run_reference(a):
+def run_reference(a, out):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -179,7 +179,7 @@ def run_reference(a):
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }  # fmt: skip
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=out, flush=True)
 
 
 def config_dict(cfg, model, op, n0, n1, S, gpus):
@@ -196,6 +196,15 @@ def config_dict(cfg, model, op, n0, n1, S, gpus):
     }
 
 
+def _claim_stdout():
+    """Library chatter (NCCL prints its version banner on stdout) must not reach the ONE JSON
+    line the driver parses: fd 1 is pointed at stderr and the line goes to the saved stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -208,8 +217,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     a = ap.parse_args()
+    out = _claim_stdout()
     if a.impl == "reference":
-        return run_reference(a)
+        return run_reference(a, out)
 
     import torch
     import torch.distributed as dist
@@ -231,6 +241,14 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def all_ranks(v: float) -> list:
+        if world == 1:
+            return [v]
+        t = torch.zeros(world, dtype=torch.float64, device="cuda")
+        t[rank] = v
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(x) for x in t.tolist()]
 
     def max_over_ranks(v: float) -> float:
         if world == 1:
@@ -280,6 +298,8 @@ def main():
             grid_ms += rep["grid_ms"]
         barrier()
     launches = int(_native.lib().inflx_kernel_launches()) - launches0
+    per_rank_ms = all_ranks(ms / a.steps)
+    per_rank_grid_ms = all_ranks(grid_ms / a.steps)
     ms = max_over_ranks(ms)
     grid_ms_max = max_over_ranks(grid_ms)
     value = total_points * a.steps / (ms / 1e3)
@@ -383,8 +403,9 @@ def main():
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu,
             "dominant_kernel_ms_per_step": grid_ms_max / a.steps,
+            "per_rank_ms_per_step": per_rank_ms, "per_rank_dominant_kernel_ms": per_rank_grid_ms,
         }  # fmt: skip
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

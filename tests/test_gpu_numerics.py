@@ -87,8 +87,9 @@ def test_speculative_division_is_ieee_whenever_it_claims_so(mod):
 def test_speculative_sqrt_is_ieee_whenever_it_claims_so(mod):
     rng = np.random.default_rng(2)
     n = 1 << 22
-    a = np.abs(_random_doubles(rng, n))
-    a[:5] = [0.0, np.inf, np.nan, -1.0, 4.0]
+    a = _random_doubles(rng, n)
+    a[: n // 2] = np.abs(a[: n // 2])
+    a[:8] = [0.0, np.inf, np.nan, -0.0, 4.0, -1.0, -1e-320, -np.inf]
     q, qe, bad = np.zeros(n), np.zeros(n), np.zeros(n, dtype=np.uint8)
     mod.launch("t_sqrt", n, [a], [q, qe, bad])
     ok = bad == 0
@@ -96,7 +97,11 @@ def test_speculative_sqrt_is_ieee_whenever_it_claims_so(mod):
     assert _same(q[ok], qe[ok]).all()
     m = (a > 1e-100) & (a < 1e100)
     assert (bad[m] == 0).all()
-    assert bad[0] == 1 and bad[1] == 1 and bad[2] == 1 and bad[3] == 1
+    # zero, inf, -0 need the slow path; a negative or NaN argument is NaN on the fast path too
+    assert bad[0] == 1 and bad[1] == 1 and bad[3] == 1
+    assert bad[2] == 0 and bad[5] == 0 and bad[7] == 0 and np.isnan(q[[2, 5, 7]]).all()
+    neg = a < -1e-300
+    assert (bad[neg] == 0).all() and np.isnan(q[neg]).all()
 
 
 def test_double_double_powers_are_correctly_rounded(mod):
