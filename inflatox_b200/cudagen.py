@@ -366,7 +366,7 @@ class GroupProgram:
         slot = self.r_slot[node]
         pair = slot // 2
         names = {k: n for n, k in self.r_slot.items()}
-        text = f"{indent}const double2 rp{pair} = __ldg(reinterpret_cast<const double2*>(rr) + {pair});\n"
+        text = f"{indent}const double2 rp{pair} = rr[{pair}];\n"
         for half, member in ((2 * pair, "x"), (2 * pair + 1, "y")):
             n = names.get(half)
             if n is not None and n not in scope:
@@ -506,7 +506,7 @@ class GroupProgram:
                 outs += self._load(r, lazy, scope, "  ") + "\n"
             outs += f"  roots[{k}] = {self._ref(r, scope)};\n"
         return (
-            "__device__ __noinline__ void inflx_slow_roots(const double* __restrict__ rr, double x1, "
+            "__device__ __noinline__ void inflx_slow_roots(const double2* __restrict__ rr, double x1, "
             "u32 pbase, double* __restrict__ roots) {\n  (void)rr; (void)x1; (void)pbase;\n"
             + body + outs + "}\n\n"
         )
@@ -542,23 +542,42 @@ class GroupProgram:
             "double* __restrict__ out, const double* __restrict__ rc, double of1, double dx1, "
             "u32 n1, u32 n_rows, u64 comp_stride, double aux) {\n"
             "  const u32 col = blockIdx.x * INFLX_BLOCK + threadIdx.x;\n"
-            "  if (col >= n1) return;\n"
             + (
                 "  const u32 s = blockIdx.z;\n  const u32 pbase = s * INFLX_NPF;\n"
                 if sweep
                 else "  const u32 s = 0;\n  const u32 pbase = 0;\n"
             )
-            + "  const double x1 = inflx_coord(col, dx1, of1);\n"
+            + "  const u32 r0 = blockIdx.y * INFLX_RPT;\n"
+            "  const u32 rows_here = min((u32)INFLX_RPT, n_rows - r0);\n"
+            # the CTA's rows of the row-frontier array: one cooperative, coalesced 128-bit copy
+            # into shared memory, overlapped with the column block; per-point reads are then
+            # conflict-free LDS.128 broadcasts instead of exposed L2 round trips
+            "#if INFLX_NRF > 0\n"
+            "  __shared__ double2 rsm[INFLX_RPT * (INFLX_NRF / 2)];\n"
+            "  {\n"
+            "    const double2* __restrict__ src = reinterpret_cast<const double2*>(\n"
+            "        rc + ((u64)s * n_rows + r0) * INFLX_NRF);\n"
+            "    for (u32 k = threadIdx.x; k < rows_here * (INFLX_NRF / 2); k += INFLX_BLOCK)\n"
+            "      rsm[k] = __ldg(src + k);\n"
+            "  }\n"
+            "#endif\n"
+            "  const bool active = col < n1;\n"
+            "  const double x1 = inflx_coord(active ? col : 0u, dx1, of1);\n"
             "  bool bad_c = false;\n"
             "  (void)x1; (void)aux; (void)comp_stride; (void)rc; (void)pbase;\n"
             + col_block
-            + "  const u32 r0 = blockIdx.y * INFLX_RPT;\n"
+            + "#if INFLX_NRF > 0\n  __syncthreads();\n#endif\n"
+            "  if (!active) return;\n"
             "#pragma unroll 1\n"
-            "  for (u32 j = 0; j < INFLX_RPT; ++j) {\n"
-            "    const u32 i = r0 + j;\n"
-            "    if (i >= n_rows) break;\n"
-            "    const u64 rowid = (u64)s * n_rows + i;\n"
-            "    const double* __restrict__ rr = rc + rowid * INFLX_NRF;\n"
+            "  for (u32 j = 0; j < rows_here; ++j) {\n"
+            "    const u64 rowid = (u64)s * n_rows + r0 + j;\n"
+            "#if defined(INFLX_EXPERIMENT_NO_SMEM)\n"
+            "    const double2* __restrict__ rr = reinterpret_cast<const double2*>(rc + rowid * INFLX_NRF);\n"
+            "#elif INFLX_NRF > 0\n"
+            "    const double2* __restrict__ rr = rsm + j * (INFLX_NRF / 2);\n"
+            "#else\n"
+            "    const double2* __restrict__ rr = nullptr;\n"
+            "#endif\n"
             "    const u64 point = rowid * n1 + col;\n"
             "    bool bad = bad_c;\n"
             f"    {decl}\n"
