@@ -1,0 +1,151 @@
+"""Randomly generated model artefacts: C text of random expression trees over x[0], x[1], args[k]
+built ONLY from + - * / sqrt fabs and pow(.,2) - the operations this back-end claims to evaluate
+bit-identically to the reference's CPU path.  The same text is compiled by gcc (reference flags,
+driven by the oracle) and by the CUDA pipeline (Compiler.build_artifact: parser -> DAG -> rate
+partition -> speculative division + slow path -> kernels).  Every finite value must agree to the
+last bit, NaN/inf patterns must be identical - for the raw model functions and for the
+arithmetic-only outputs of complete_analysis (consistency, eps_V, eps_H, omega)."""
+import ctypes
+import os
+import random
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+import oracle
+from inflatox_b200 import libinflx_rs as rs
+from inflatox_b200.compiler import Compiler
+
+pytestmark = pytest.mark.gpu
+
+N_PAR = 3
+PREAMBLE = """#include <math.h>
+#include <stdint.h>
+const uint16_t VERSION[3] = {5,0,0};
+const uint32_t DIM = 2;
+const uint32_t N_PARAMETERS = %d;
+char *const MODEL_NAME = "random%d";
+const char USE_GSL = 0;
+
+"""
+
+
+def rand_expr(rng: random.Random, depth: int) -> str:
+    if depth <= 0 or rng.random() < 0.15:
+        r = rng.random()
+        if r < 0.35:
+            return "x[0]"
+        if r < 0.7:
+            return "x[1]"
+        if r < 0.85:
+            return f"args[{rng.randrange(N_PAR)}]"
+        return rng.choice(["2", "3", "0.5", "1.25", "7", "(1.0/3.0)", "10"])
+    r = rng.random()
+    a, b = rand_expr(rng, depth - 1), rand_expr(rng, depth - 1)
+    if r < 0.25:
+        return f"({a} + {b})"
+    if r < 0.45:
+        return f"({a} - {b})"
+    if r < 0.7:
+        return f"({a})*({b})"
+    if r < 0.88:
+        return f"({a})/({b})"
+    if r < 0.94:
+        return f"sqrt(fabs({a}) + 0.125)"
+    if r < 0.97:
+        return f"sqrt({a})"  # may be NaN: legit
+    return f"pow({a}, 2)"
+
+
+def make_unit(seed: int) -> str:
+    rng = random.Random(seed)
+    xa = "(const double x[], const double args[])"
+    text = PREAMBLE % (N_PAR, seed)
+    for name in ("V", "v00", "v01", "v10", "v11", "grad_norm_squared"):
+        text += f"double {name}{xa}{{\n    return {rand_expr(rng, rng.randint(3, 6))};\n}}\n\n"
+    text += (
+        "double inner_prod(const double x[], const double args[], const double v1[], "
+        "const double v2[]){\n    const double g00 = 1;\n    const double g11 = 1;\n"
+        "    return 0.0 + (g00 * v1[0] * v2[0]) + (g11 * v1[1] * v2[1]);\n}\n\n"
+    )
+    for name in ("v", "w1"):
+        text += (
+            f"void {name}(const double x[], const double args[], double v_out[]){{\n"
+            f"    v_out[0] = {rand_expr(rng, 3)};\n    v_out[1] = {rand_expr(rng, 3)};\n    return;\n}}\n\n"
+        )
+    return text
+
+
+class _RawOracle(oracle.Oracle):
+    """oracle driver over an arbitrary generated C unit (same reference flag set)."""
+
+    def __init__(self, c_text: str, workdir: str):
+        src = os.path.join(workdir, "model.c")
+        so = os.path.join(workdir, "model.so")
+        with open(src, "w") as fh:
+            fh.write(c_text)
+        subprocess.run(
+            ["gcc", "-o", so, src, *[f for f in oracle.REFERENCE_FLAGS if f != "-Werror"],
+             "-ffp-contract=off"], check=True)  # fmt: skip
+        b = oracle._Build()
+        self.quad, self.sfx = False, ""
+        self.lib = ctypes.CDLL(b.driver(False))
+        self.path, self.h = so, ctypes.c_void_p()
+        fn = self.lib.oracle_open
+        fn.restype = ctypes.c_int
+        assert fn(so.encode(), ctypes.byref(self.h)) == 0
+        self.n_fields, self.n_params, self.meta = 2, N_PAR, {}
+
+
+def _bit_identical(a, b):
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    nan = np.isnan(a) & np.isnan(b)
+    return (a.view(np.uint64) == b.view(np.uint64)) | nan | ((a == 0) & (b == 0))
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_arithmetic_models_are_bit_identical(seed, tmp_path):
+    c_text = make_unit(seed)
+    orc = _RawOracle(c_text, str(tmp_path))
+    comp = Compiler.__new__(Compiler)
+    comp.nvrtc_opts = list(Compiler.default_nvrtc_flags)
+    comp.output_path = str(tmp_path / "model.c")
+    art_path = str(tmp_path / "model.bin")
+    comp.build_artifact(c_text, art_path)
+    lib = rs.open_inflx_dylib(art_path, False)
+    lib.set_devices([0])
+    rng = np.random.default_rng(seed)
+    p = rng.uniform(0.5, 3.0, N_PAR)
+    ext = (-2.0, 3.0, -1.5, 2.5)
+    n0, n1 = 67, 139
+    ss = np.array(ext).reshape(2, 2)
+    # raw model functions
+    v = np.zeros((n0, n1))
+    lib.potential_array(v, p, ss)
+    assert _bit_identical(v, orc.potential_array(p, n0, n1, ext)).all()
+    h = lib.hesse_array(np.array([n0, n1]), p, ss)
+    assert _bit_identical(h, orc.hesse_array(p, n0, n1, ext)).all()
+    # closed forms: every output except delta (atan) and eta (tan) is pure IEEE arithmetic
+    out = np.zeros((n0, n1, 6))
+    rs.complete_analysis(lib, p, out, ss, False, 0)
+    ref = orc.complete_analysis(p, n0, n1, ext)
+    for k in (0, 1, 2, 5):
+        same = _bit_identical(out[..., k], ref[..., k])
+        assert same.all(), (seed, k, int((~same).sum()), out[..., k][~same][:3], ref[..., k][~same][:3])
+    # delta = atan(.) and eta = omega*tan(delta) - 3 go through the atan/tan helper (<= 1 / 3 ulp)
+    for k in (3, 4):
+        assert (np.isnan(out[..., k]) == np.isnan(ref[..., k])).all()
+        assert (np.isinf(out[..., k]) == np.isinf(ref[..., k])).all()
+    fin = np.isfinite(ref[..., 4]) & np.isfinite(out[..., 4])
+    assert (np.abs(out[..., 4][fin] - ref[..., 4][fin]) <= 4.5e-16 * np.abs(ref[..., 4][fin])).all()
+    fin = np.isfinite(ref[..., 3]) & np.isfinite(out[..., 3])
+    d_eta = np.abs(out[..., 3][fin] - ref[..., 3][fin])
+    assert (d_eta <= 1.5e-15 * (np.abs(ref[..., 3][fin]) + 3.0)).all(), d_eta.max()
+    c1 = np.zeros((n0, n1))
+    rs.consistency_only(lib, p, c1, ss, False, 0)
+    assert _bit_identical(c1, orc.consistency_only(p, n0, n1, ext)).all()
+    ev = np.zeros((n0, n1))
+    rs.epsilon_v_only(lib, p, ev, ss, False, 0)
+    assert _bit_identical(ev, orc.epsilon_v_only(p, n0, n1, ext)).all()
