@@ -142,7 +142,9 @@ def test_random_arithmetic_models_are_bit_identical(seed, tmp_path):
     assert (np.abs(out[..., 4][fin] - ref[..., 4][fin]) <= 4.5e-16 * np.abs(ref[..., 4][fin])).all()
     fin = np.isfinite(ref[..., 3]) & np.isfinite(out[..., 3])
     d_eta = np.abs(out[..., 3][fin] - ref[..., 3][fin])
-    assert (d_eta <= 1.5e-15 * (np.abs(ref[..., 3][fin]) + 3.0)).all(), d_eta.max()
+    # tan amplifies the (<= 1 ulp) difference between two correctly working atan's by tan(delta)
+    amp = 1.0 + np.abs(np.tan(ref[..., 4][fin]))
+    assert (d_eta <= 1.5e-15 * amp * (np.abs(ref[..., 3][fin]) + 3.0)).all(), d_eta.max()
     c1 = np.zeros((n0, n1))
     rs.consistency_only(lib, p, c1, ss, False, 0)
     assert _bit_identical(c1, orc.consistency_only(p, n0, n1, ext)).all()
