@@ -12,7 +12,7 @@ All functions of one translation unit are interned into ONE DAG (`Dag`).  Struct
 sub-expressions — across `V`, `v00..v11`, `grad_norm_squared`, the basis vectors — collapse to one
 node.  That is the "joint common-subexpression reuse" of the CUDA back-end, and it is value
 preserving by construction: a node is shared only if it is the same operation on the same
-operands.
+operands (up to the operand order of the commutative `+` and `*`, which IEEE arithmetic ignores).
 
 Constant folding follows what gcc/clang do at -O3 *without* -ffast-math but with the reference's
 `-fno-math-errno -fno-signed-zeros` (compiler.py:299-310; checked against gcc 13.3 assembly):
@@ -176,6 +176,10 @@ class Dag:
             if cb and _is_pow2(self.cval(b)):
                 # x / 2^k == x * 2^-k exactly (gcc does this too); keeps a divide off the fp64 pipe
                 return self.binop("*", a, self.const(1.0 / self.cval(b)))
+        if op in "+*" and a > b:
+            # IEEE addition and multiplication are commutative bit for bit: one canonical operand
+            # order lets `a*b` and `b*a` (sympy emits both across functions) share a node
+            a, b = b, a
         return self._intern((op, a, b), (op, a, b))
 
     def call(self, name: str, args: list[int]) -> int:
