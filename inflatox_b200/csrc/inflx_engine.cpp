@@ -23,6 +23,10 @@
 #include <thread>
 #include <vector>
 
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
+
 #include "../../include/inflx_b200.h"
 #include "inflx_cuda_dl.h"
 
@@ -209,13 +213,50 @@ static inflx_status get_device(int ordinal, DeviceState** out) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// a tiny fork-join pool for the staged (pageable destination) copy-out
+// staged (pageable destination) copy-out: pinned staging buffer -> caller's array, in parallel
+// and with non-temporal stores (the destination is written once and not read back here, so
+// streaming stores save the read-for-ownership traffic of a plain memcpy)
 // ---------------------------------------------------------------------------------------------
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) static void stream_copy_avx2(char* d, const char* s, size_t n) {
+  size_t head = (32 - (reinterpret_cast<uintptr_t>(d) & 31)) & 31;
+  if (head > n) head = n;
+  memcpy(d, s, head);
+  d += head;
+  s += head;
+  n -= head;
+  const size_t blocks = n / 128;
+  for (size_t i = 0; i < blocks; ++i, s += 128, d += 128) {
+    const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(s));
+    const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(s + 32));
+    const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(s + 64));
+    const __m256i e = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(s + 96));
+    _mm256_stream_si256(reinterpret_cast<__m256i*>(d), a);
+    _mm256_stream_si256(reinterpret_cast<__m256i*>(d + 32), b);
+    _mm256_stream_si256(reinterpret_cast<__m256i*>(d + 64), c);
+    _mm256_stream_si256(reinterpret_cast<__m256i*>(d + 96), e);
+  }
+  _mm_sfence();
+  memcpy(d, s, n - blocks * 128);
+}
+#endif
+
+static void copy_out(char* d, const char* s, size_t n) {
+#if defined(__x86_64__)
+  static const bool avx2 = __builtin_cpu_supports("avx2");
+  if (avx2 && n >= 4096) {
+    stream_copy_avx2(d, s, n);
+    return;
+  }
+#endif
+  memcpy(d, s, n);
+}
+
 static void parallel_memcpy(void* dst, const void* src, size_t bytes) {
   static const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-  unsigned n = (unsigned)std::min<size_t>(std::min(hw, 16u), bytes / (4u << 20));
+  unsigned n = (unsigned)std::min<size_t>(std::min(hw, 16u), bytes / (2u << 20));
   if (n <= 1) {
-    memcpy(dst, src, bytes);
+    copy_out((char*)dst, (const char*)src, bytes);
     return;
   }
   std::vector<std::thread> th;
@@ -224,7 +265,7 @@ static void parallel_memcpy(void* dst, const void* src, size_t bytes) {
     size_t b = (size_t)i * per;
     if (b >= bytes) break;
     size_t e = std::min(bytes, b + per);
-    th.emplace_back([=] { memcpy((char*)dst + b, (const char*)src + b, e - b); });
+    th.emplace_back([=] { copy_out((char*)dst + b, (const char*)src + b, e - b); });
   }
   for (auto& t : th) t.join();
 }
