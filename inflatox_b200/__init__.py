@@ -24,3 +24,19 @@ __all__ = [
     "__version__",
     "__abi_version__",
 ]
+
+
+def __getattr__(name):
+    # `InflationModelBuilder` (reference python/inflatox/symbolic.py) is upstream of the hot path
+    # and not re-implemented; hand out the reference's when that package is installed.
+    if name == "InflationModelBuilder":
+        try:
+            from inflatox import InflationModelBuilder  # type: ignore
+        except ImportError as e:
+            raise ImportError(
+                "InflationModelBuilder is the reference package's symbolic front-end "
+                "(`pip install inflatox`); inflatox_b200 accelerates the numerical path and takes "
+                "its InflationModel objects (or InflationModel.load fixtures) as input"
+            ) from e
+        return InflationModelBuilder
+    raise AttributeError(name)

@@ -244,6 +244,11 @@ class GroupProgram:
                 or any(u in grid_set and self.klass(u) != "R" for u in users.get(i, ()))
             )
         ]
+        if len(self.p_frontier) > PC_CAPACITY:
+            raise Exception(
+                f"model needs {len(self.p_frontier)} parameter-class values per vector; the "
+                f"__constant__ bank holds {PC_CAPACITY}"
+            )
         self.p_slot = {n: k for k, n in enumerate(self.p_frontier)}
         self.r_slot = {n: k for k, n in enumerate(self.r_frontier)}
         # rows of the row-frontier array are read with 128-bit loads: keep them 16-byte aligned

@@ -320,9 +320,12 @@ class _PinnedLease:
         self.block = block
 
     def __del__(self):
-        pool = _pin_pool.setdefault(self.block.nbytes, [])
-        if len(pool) < 4:
-            pool.append(self.block)
+        try:
+            pool = _pin_pool.setdefault(self.block.nbytes, [])
+            if len(pool) < 4:
+                pool.append(self.block)
+        except Exception:  # interpreter shutdown: module globals may already be gone
+            pass
 
 
 def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
