@@ -39,6 +39,10 @@ from .cexpr import Dag, ParsedUnit
 
 _CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 
+# resident CTAs per SM the register allocation of a group's grid kernels must allow (128-thread
+# CTAs: 5 -> 96 registers, 6 -> 80).  From the tools/tune.py sweeps over the five test models: the
+# six-output kernels are fastest at 6, the single-plane ones at 5.
+MIN_BLOCKS = {"cmp": 6, "hes": 6}
 PC_CAPACITY = 7680  # doubles of __constant__ memory for P-frontier values (60 of the 64 KiB)
 MAX_FAST_POW = 64  # |exponent| up to which literal (half-)integer powers use the dd chains
 
@@ -391,7 +395,7 @@ class GroupProgram:
         with open(os.path.join(_CSRC, "inflx_device.cuh")) as fh:
             device_header = fh.read()
         npf, nrf = len(self.p_frontier), self.n_row_slots
-        src = [device_header]
+        src = [f"#define INFLX_GROUP_MIN_BLOCKS {MIN_BLOCKS.get(self.group, 5)}\n", device_header]
         src.append(f'\n// ===== generated: model "{model_name}", group "{self.group}" =====\n')
         src.append(f"#define INFLX_NP {self.n_params}\n#define INFLX_NPF {npf}\n")
         src.append(f"#define INFLX_NRF {nrf}\n#define INFLX_PC_CAP {PC_CAPACITY}\n")

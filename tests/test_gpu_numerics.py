@@ -125,6 +125,15 @@ def test_double_double_powers_are_correctly_rounded(mod):
         assert p4[k] == nearest(x**4)
         assert p7[k] == nearest(x**7)
         assert pm2[k] == nearest(1 / x**2)
+    # irregular arguments of the half-integer powers (exact policy = what the slow path runs)
+    special = np.array([0.0, np.inf, -1.0, np.nan, 1e-320, 1e300, 4.0])
+    outs2 = [np.zeros(special.size) for _ in range(6)]
+    mod.launch("t_pow", special.size, [special], outs2)
+    ph2, pmh2 = outs2[4], outs2[5]
+    assert ph2[0] == 0.0 and ph2[1] == np.inf and np.isnan(ph2[2]) and np.isnan(ph2[3])
+    assert pmh2[0] == np.inf and pmh2[1] == 0.0 and np.isnan(pmh2[2]) and np.isnan(pmh2[3])
+    assert ph2[6] == 8.0 and pmh2[6] == 0.5
+    assert abs(pmh2[4] / (1e-320 ** -0.5) - 1) < 1e-15 and abs(pmh2[5] / 1e-150 - 1) < 1e-15
     # half-integer powers: compare with a 200-bit evaluation
     import mpmath
 
