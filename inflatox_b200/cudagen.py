@@ -322,10 +322,15 @@ class GroupProgram:
         k = n[0]
         pol = "inflx_spec(bad)" if spec else "inflx_exact()"
         if k == "rcp":
-            return f"inflx_rcp_s({self._ref(n[1], scope)})"
+            # a reciprocal read by a faster class carries the denominator's validity (NaN if not)
+            hoisted = any(self.klass(u) != self.klass(i) for u in self.users.get(i, ()))
+            fn = "inflx_rcp_checked" if hoisted else "inflx_rcp_s"
+            return f"{fn}({self._ref(n[1], scope)})"
         if k == "/" and spec:
-            y = self._ref(self.rcp_of[n[2]], scope)
-            return f"inflx_div_y({self._ref(n[1], scope)}, {self._ref(n[2], scope)}, {y}, bad)"
+            rcp = self.rcp_of[n[2]]
+            fn = "inflx_div_yh" if self.klass(rcp) != self.klass(i) else "inflx_div_y"
+            y = self._ref(rcp, scope)
+            return f"{fn}({self._ref(n[1], scope)}, {self._ref(n[2], scope)}, {y}, bad)"
         if k in ("+", "-", "*", "/"):
             return f"{self._ref(n[1], scope)} {k} {self._ref(n[2], scope)}"
         if k == "neg":

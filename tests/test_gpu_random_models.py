@@ -151,3 +151,81 @@ def test_random_arithmetic_models_are_bit_identical(seed, tmp_path):
     ev = np.zeros((n0, n1))
     rs.epsilon_v_only(lib, p, ev, ss, False, 0)
     assert _bit_identical(ev, orc.epsilon_v_only(p, n0, n1, ext)).all()
+
+
+SPECIAL_UNIT = PREAMBLE % (N_PAR, 999) + """
+double V(const double x[], const double args[]){
+    return (x[1] + 2)/(x[0]) + (x[1])/(args[0]*x[0]) + (x[0])/(x[1]);
+}
+double v00(const double x[], const double args[]){
+    return (x[1])/(args[1]) + sqrt(x[0] - 1)*x[1];
+}
+double v01(const double x[], const double args[]){
+    return (x[1]*x[0])/(args[2]);
+}
+double v10(const double x[], const double args[]){
+    return (x[0] - x[1])/((x[0])*(x[0]) - 1);
+}
+double v11(const double x[], const double args[]){
+    return (1.0/3.0)/(x[1]) + (x[0])/(args[0]);
+}
+double grad_norm_squared(const double x[], const double args[]){
+    return ((x[1])/(x[0]))/(x[1] - x[0]);
+}
+double inner_prod(const double x[], const double args[], const double v1[], const double v2[]){
+    const double g00 = 1;
+    const double g11 = 1;
+    return 0.0 + (g00 * v1[0] * v2[0]) + (g11 * v1[1] * v2[1]);
+}
+void v(const double x[], const double args[], double v_out[]){
+    v_out[0] = x[0];
+    v_out[1] = x[1];
+    return;
+}
+void w1(const double x[], const double args[], double v_out[]){
+    v_out[0] = x[1];
+    v_out[1] = x[0];
+    return;
+}
+"""
+
+
+@pytest.mark.parametrize(
+    "params",
+    [[1.0, 2.0, 3.0], [1e308, 0.0, 1e-320], [np.inf, -0.0, np.nan], [3e-310, 1e300, 5e-324]],
+)
+def test_irregular_operands_take_the_exact_path(params, tmp_path):
+    """Zero, infinite, subnormal, huge and NaN denominators / numerators in every class (parameter,
+    row, column, per point): the speculative division must hand these points to the IEEE slow
+    path - results, including the signs of infinities, equal gcc's bit for bit."""
+    orc = _RawOracle(SPECIAL_UNIT, str(tmp_path))
+    comp = Compiler.__new__(Compiler)
+    comp.nvrtc_opts = list(Compiler.default_nvrtc_flags)
+    comp.output_path = str(tmp_path / "model.c")
+    art_path = str(tmp_path / "model.bin")
+    comp.build_artifact(SPECIAL_UNIT, art_path)
+    lib = rs.open_inflx_dylib(art_path, False)
+    lib.set_devices([0])
+    p = np.array(params, dtype=np.float64)
+    ext = (-1.0, 3.0, -2.0, 2.0)  # the grid contains x0 = 0, x0 = +-1, x1 = 0 and x0 = x1 exactly
+    n0, n1 = 16, 32
+    ss = np.array(ext).reshape(2, 2)
+
+    def same(a, b):
+        a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+        return (a.view(np.uint64) == b.view(np.uint64)) | (np.isnan(a) & np.isnan(b)) | ((a == 0) & (b == 0))
+
+    v = np.zeros((n0, n1))
+    lib.potential_array(v, p, ss)
+    ref = orc.potential_array(p, n0, n1, ext)
+    assert same(v, ref).all(), (v[~same(v, ref)][:4], ref[~same(v, ref)][:4])
+    h = lib.hesse_array(np.array([n0, n1]), p, ss)
+    assert same(h, orc.hesse_array(p, n0, n1, ext)).all()
+    out = np.zeros((n0, n1, 6))
+    rs.complete_analysis(lib, p, out, ss, False, 0)
+    ref = orc.complete_analysis(p, n0, n1, ext)
+    for k in (0, 1, 2, 5):
+        ok = same(out[..., k], ref[..., k])
+        assert ok.all(), (k, out[..., k][~ok][:4], ref[..., k][~ok][:4])
+    assert (np.isnan(out[..., 3:5]) == np.isnan(ref[..., 3:5])).all()
+    assert (np.isinf(out[..., 3:5]) == np.isinf(ref[..., 3:5])).all()

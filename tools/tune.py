@@ -36,7 +36,7 @@ def main():
         flags = ["--gpu-architecture=sm_100a", "--std=c++17",
                  f"--fmad={'true' if v.get('fmad') else 'false'}", "--prec-div=true",
                  "--prec-sqrt=true", "-lineinfo", f"-DINFLX_RPT={v['rpt']}",
-                 f"-DINFLX_BLOCK={v['block']}", f"-DINFLX_MIN_BLOCKS={v['minb']}"] + v.get("extra", [])
+                 f"-DINFLX_BLOCK={v["block"]}"] + ([f"-DINFLX_MIN_BLOCKS={v["minb"]}"] if "minb" in v else []) + v.get("extra", [])
         try:
             art = ix.Compiler(m, silent=True, cse=cse, compiler_flags=flags).compile()
         except Exception as e:
