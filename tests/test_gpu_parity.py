@@ -257,3 +257,53 @@ def test_multi_device_row_sharding_in_one_process():
     rep = rs.grid_eval(lib, "complete_analysis", p, many, N0, N1, ext)
     assert rep["n_devices"] == n_dev
     assert np.array_equal(one, many, equal_nan=True)
+
+
+@pytest.mark.parametrize("model", ["angular", "egno", "d5"])
+def test_reference_test_flows_through_the_facade(model):
+    """The call sequences of the reference's integration tests (tests/test_angular.py:62-86,
+    test_egno.py:79-105, test_d5.py:143-173) through the unchanged public API: same arguments,
+    same return shapes; plus the oracle on what they return."""
+    from inflatox_b200.consistency_conditions import GeneralisedAL
+
+    anguelova = GeneralisedAL(cases.artifact(model))
+    args, extent = cases.params(model), cases.EXTENT[model]
+    N = 100
+    orc = oracle.Oracle(model)
+    v = anguelova.calc_V_array(args, [extent[0], extent[2]], [extent[1], extent[3]], [N, N])
+    assert v.shape == (N, N)
+    check(model, v, orc.potential_array(args, N, N, extent), min_frac=0.999, what="calc_V_array")
+    out = anguelova.complete_analysis(args, *extent, *[N, N])
+    assert len(out) == 6 and all(o.shape == (N, N) for o in out)
+    ref = orc.complete_analysis(args, N, N, extent)
+    for k in range(6):
+        check(model, out[k], ref[..., k], min_frac=0.97, what=f"facade plane {k}")
+    traj = cases.trajectory(model)
+    ot = anguelova.complete_analysis_ot(args, traj)
+    assert len(ot) == 6 and ot[0].shape == (traj.shape[0], 1)
+    rt = anguelova.consistency_rapidturn(args, *extent, *[N, N])
+    check(model, rt, orc.consistency_rapidturn_only(args, N, N, extent), min_frac=0.97, what="rapidturn")
+    assert anguelova.consistency(args, *extent, N, N).shape == (N, N)
+    assert anguelova.epsilon_v(args, *extent, N, N).shape == (N, N)
+    assert anguelova.consistency_ot(args, traj).shape == (traj.shape[0],)
+    assert anguelova.epsilon_v_ot(args, traj).shape == (traj.shape[0],)
+    assert anguelova.consistency_rapidturn_ot(args, traj).shape == (traj.shape[0],)
+    flags = anguelova.flag_quantum_dif(args, *extent, N, N, accuracy=0.5)
+    assert flags.dtype == bool and flags.shape == (N, N)
+    h = anguelova.calc_H_array(args, [extent[0], extent[2]], [extent[1], extent[3]], [N, N])
+    assert h.shape == (2, 2, N, N)
+    if model == "d5":
+        # the reference walks the axes from `stop` outwards (src/lib.rs:250-258); for d5 that leaves
+        # the model's domain, where w1 degenerates into v - the reference-generated C says the
+        # same (oracle: <v, w1> = 1 at [58.5, 0]), so the reference raises BasisOth here as well
+        with pytest.raises(Exception, match="to be orthogonal everywhere"):
+            anguelova.validate_basis_on_domain(args, [extent[0], extent[2]], [extent[1], extent[3]], N=8)
+        x = np.array([58.5, 0.0])
+        v, w = orc.basis(0, x, args), orc.basis(1, x, args)
+        assert abs(orc.inner_prod(x, args, v, w) - 1.0) < 1e-12
+    else:
+        anguelova.validate_basis_on_domain(args, [extent[0], extent[2]], [extent[1], extent[3]], N=8)
+    sw = anguelova.sweep_complete_analysis(np.stack([args, args * 1.01]), *extent, 24, 40)
+    assert sw.shape == (2, 24, 40, 6)
+    assert np.array_equal(sw[0], np.stack(anguelova.complete_analysis(args, *extent, 24, 40), axis=-1),
+                          equal_nan=True)
