@@ -74,12 +74,6 @@ GROUPS = {
     "hes": (("v00", "v01", "v10", "v11"), (), ("hesse",), ("hesse",)),
 }
 
-OUT_DOUBLES = {  # doubles (or bytes for the flag) written per point
-    "complete_analysis": 6, "consistency_only": 1, "consistency_rapidturn_only": 1,
-    "epsilon_v_only": 1, "flag_quantum_dif": 1, "potential": 1, "hesse": 4, "basis": 7,
-}  # fmt: skip
-
-
 def _lit(v: float) -> str:
     if math.isnan(v):
         return "(0.0/0.0)"
