@@ -71,7 +71,7 @@ class CParseError(Exception):
 _TOKEN_RE = re.compile(
     r"\s*(?:(?P<num>(?:\d+\.\d*|\.\d+|\d+)(?:[eE][+-]?\d+)?)"
     r"|(?P<id>[A-Za-z_][A-Za-z_0-9]*)"
-    r"|(?P<op>[-+*/()\[\],=;]))"
+    r"|(?P<op><=|>=|==|!=|&&|\|\||[-+*/()\[\],=;<>!?:]))"
 )
 
 
@@ -90,6 +90,10 @@ class Dag:
     ("v1", k) / ("v2", k)   inner_prod's vector arguments
     ("+", a, b) ("-", a, b) ("*", a, b) ("/", a, b) ("neg", a)
     ("f", name, a[, b])     libm call
+    ("cmp", op, a, b)       C comparison (< > <= >= == !=): 1.0 if it holds, else 0.0
+    ("and", a, b) ("or", a, b) ("not", a)   C logical operators on "non-zero is true"
+    ("sel", c, a, b)        c ? a : b (c non-zero selects a); both arms are pure, so evaluating
+                            both and selecting is what the C code means
     """
 
     def __init__(self):
@@ -182,6 +186,35 @@ class Dag:
             a, b = b, a
         return self._intern((op, a, b), (op, a, b))
 
+    # -- conditionals (sympy prints Piecewise / sign / Heaviside with these) ----------------------
+    def cmp(self, op: str, a: int, b: int) -> int:
+        a, b = self.to_double(a), self.to_double(b)
+        if self.is_const(a) and self.is_const(b):
+            x, y = self.cval(a), self.cval(b)
+            r = {"<": x < y, ">": x > y, "<=": x <= y, ">=": x >= y, "==": x == y, "!=": x != y}[op]
+            return self.const(1.0 if r else 0.0)
+        return self._intern(("cmp", op, a, b), ("cmp", op, a, b))
+
+    def logical(self, op: str, a: int, b: int | None = None) -> int:
+        a = self.to_double(a)
+        if op == "not":
+            if self.is_const(a):
+                return self.const(0.0 if self.cval(a) != 0.0 else 1.0)
+            return self._intern(("not", a), ("not", a))
+        b = self.to_double(b)
+        if self.is_const(a) and self.is_const(b):
+            x, y = self.cval(a) != 0.0, self.cval(b) != 0.0
+            return self.const(1.0 if ((x and y) if op == "and" else (x or y)) else 0.0)
+        return self._intern((op, a, b), (op, a, b))
+
+    def select(self, c: int, a: int, b: int) -> int:
+        c, a, b = self.to_double(c), self.to_double(a), self.to_double(b)
+        if self.is_const(c):
+            return a if self.cval(c) != 0.0 else b
+        if a == b:
+            return a
+        return self._intern(("sel", c, a, b), ("sel", c, a, b))
+
     def call(self, name: str, args: list[int]) -> int:
         if name not in LIBM_FUNCTIONS:
             raise UnsupportedFunctionError(
@@ -222,10 +255,16 @@ class Dag:
         k = n[0]
         if k in ("+", "-", "*", "/"):
             return (n[1], n[2])
-        if k == "neg":
+        if k in ("neg", "not"):
             return (n[1],)
         if k == "f":
             return tuple(n[2:])
+        if k == "cmp":
+            return (n[2], n[3])
+        if k in ("and", "or"):
+            return (n[1], n[2])
+        if k == "sel":
+            return (n[1], n[2], n[3])
         return ()
 
     def reachable(self, roots) -> list[int]:
@@ -357,10 +396,49 @@ class _ExprParser:
             raise CParseError(f"expected {val!r}, found {v!r} in function {self.fn.name}")
 
     def parse(self) -> int:
-        e = self._additive()
+        e = self._conditional()
         if self.i != len(self.toks):
             raise CParseError(f"trailing tokens in expression of {self.fn.name}: {self._peek()}")
         return e
+
+    # C precedence, lowest first: ?:  ||  &&  == !=  < > <= >=  + -  * /  unary
+    def _conditional(self) -> int:
+        c = self._logical_or()
+        if self._peek()[1] == "?":
+            self._next()
+            a = self._conditional()
+            self._expect(":")
+            b = self._conditional()
+            return self.dag.select(c, a, b)
+        return c
+
+    def _logical_or(self) -> int:
+        lhs = self._logical_and()
+        while self._peek()[1] == "||":
+            self._next()
+            lhs = self.dag.logical("or", lhs, self._logical_and())
+        return lhs
+
+    def _logical_and(self) -> int:
+        lhs = self._equality()
+        while self._peek()[1] == "&&":
+            self._next()
+            lhs = self.dag.logical("and", lhs, self._equality())
+        return lhs
+
+    def _equality(self) -> int:
+        lhs = self._relational()
+        while self._peek()[1] in ("==", "!="):
+            op = self._next()[1]
+            lhs = self.dag.cmp(op, lhs, self._relational())
+        return lhs
+
+    def _relational(self) -> int:
+        lhs = self._additive()
+        while self._peek()[1] in ("<", ">", "<=", ">="):
+            op = self._next()[1]
+            lhs = self.dag.cmp(op, lhs, self._additive())
+        return lhs
 
     def _additive(self) -> int:
         lhs = self._multiplicative()
@@ -386,6 +464,9 @@ class _ExprParser:
         if v == "+":
             self._next()
             return self._unary()
+        if v == "!":
+            self._next()
+            return self.dag.logical("not", self._unary())
         return self._primary()
 
     def _index(self) -> int:
@@ -403,7 +484,7 @@ class _ExprParser:
                 return self.dag.iconst(int(v))
             return self.dag.const(float(v))
         if v == "(":
-            e = self._additive()
+            e = self._conditional()
             self._expect(")")
             return e
         if k == "id":
@@ -418,10 +499,10 @@ class _ExprParser:
                 self._next()
                 args = []
                 if self._peek()[1] != ")":
-                    args.append(self._additive())
+                    args.append(self._conditional())
                     while self._peek()[1] == ",":
                         self._next()
-                        args.append(self._additive())
+                        args.append(self._conditional())
                 self._expect(")")
                 return self.dag.call(v, args)
             if v in self.env:
@@ -458,8 +539,15 @@ def parse_c_unit(text: str, constants: dict[str, str] | None = None) -> ParsedUn
         unit.use_gsl = int(m.group(1))
 
     cur: ParsedFunction | None = None
+    pending = ""
     for raw in text.split("\n"):
         line = raw.strip()
+        if cur is not None and line != "}" and not line.startswith("//"):
+            # a statement may span several lines (sympy prints Piecewise that way): join up to ';'
+            pending = (pending + " " + line).strip() if pending else line
+            if pending and not pending.endswith(";"):
+                continue
+            line, pending = pending, ""
         if cur is None:
             fm = _FUNC_RE.match(line)
             if fm:

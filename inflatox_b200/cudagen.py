@@ -253,7 +253,9 @@ class GroupProgram:
         self.n_row_slots = (len(self.r_frontier) + 1) & ~1
 
     def is_op(self, i: int) -> bool:
-        return self.node(i)[0] in ("+", "-", "*", "/", "neg", "f", "rcp")
+        return self.node(i)[0] in (
+            "+", "-", "*", "/", "neg", "f", "rcp", "cmp", "and", "or", "not", "sel"
+        )  # fmt: skip
 
     def nodes_of(self, classes: str, within=None) -> list[int]:
         src = self.all_nodes if within is None else within
@@ -329,6 +331,23 @@ class GroupProgram:
             return f"{self._ref(n[1], scope)} {k} {self._ref(n[2], scope)}"
         if k == "neg":
             return f"-{self._ref(n[1], scope)}"
+        if k == "cmp":
+            return f"(({self._ref(n[2], scope)} {n[1]} {self._ref(n[3], scope)}) ? 1.0 : 0.0)"
+        if k in ("and", "or"):
+            op = "&&" if k == "and" else "||"
+            return (
+                f"((({self._ref(n[1], scope)} != 0.0) {op} ({self._ref(n[2], scope)} != 0.0)) "
+                "? 1.0 : 0.0)"
+            )
+        if k == "not":
+            return f"(({self._ref(n[1], scope)} == 0.0) ? 1.0 : 0.0)"
+        if k == "sel":
+            # both arms are already evaluated (pure expressions); NaN / inf in the arm that is
+            # not taken is discarded by the select exactly as the C conditional discards it
+            return (
+                f"(({self._ref(n[1], scope)} != 0.0) ? {self._ref(n[2], scope)} : "
+                f"{self._ref(n[3], scope)})"
+            )
         if k == "f":
             name = n[1]
             args = [self._ref(a, scope) for a in n[2:]]

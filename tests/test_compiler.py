@@ -148,3 +148,15 @@ def test_flops_per_point_are_frozen():
     for model, f in want.items():
         assert cases.artifact(model).flops_per_point("complete_analysis") == f
     assert cases.artifact("angular").flops_per_point("consistency_only") == 205
+
+
+def test_piecewise_models_compile():
+    """sympy prints Piecewise / sign / Heaviside as (multi-line) C conditionals; the parser, the
+    DAG and the CUDA emitter carry them (cmp / and / or / not / sel nodes)."""
+    m = ix.InflationModel.load(os.path.join(cases.GOLDEN, "models", "doc.pkl.gz"))
+    r, th = m.coordinates
+    m.potential = m.potential + sympy.Piecewise((r**2, r > 1), (sympy.sign(th) * th, True))
+    comp = ix.Compiler(m, silent=True)
+    art = comp.compile()
+    assert "?" in comp.c_source and art.n_parameters == 1
+    assert read_artifact_metadata(art.shared_object_path)["flops_per_point"]["potential"] > 7

@@ -5,11 +5,6 @@ driven by the oracle) and by the CUDA pipeline (Compiler.build_artifact: parser 
 partition -> speculative division + slow path -> kernels).  Every finite value must agree to the
 last bit, NaN/inf patterns must be identical - for the raw model functions and for the
 arithmetic-only outputs of complete_analysis (consistency, eps_V, eps_H, omega)."""
-import ctypes
-import os
-import random
-import subprocess
-import tempfile
 
 import numpy as np
 import pytest
@@ -20,83 +15,7 @@ from inflatox_b200.compiler import Compiler
 
 pytestmark = pytest.mark.gpu
 
-N_PAR = 3
-PREAMBLE = """#include <math.h>
-#include <stdint.h>
-const uint16_t VERSION[3] = {5,0,0};
-const uint32_t DIM = 2;
-const uint32_t N_PARAMETERS = %d;
-char *const MODEL_NAME = "random%d";
-const char USE_GSL = 0;
-
-"""
-
-
-def rand_expr(rng: random.Random, depth: int) -> str:
-    if depth <= 0 or rng.random() < 0.15:
-        r = rng.random()
-        if r < 0.35:
-            return "x[0]"
-        if r < 0.7:
-            return "x[1]"
-        if r < 0.85:
-            return f"args[{rng.randrange(N_PAR)}]"
-        return rng.choice(["2", "3", "0.5", "1.25", "7", "(1.0/3.0)", "10"])
-    r = rng.random()
-    a, b = rand_expr(rng, depth - 1), rand_expr(rng, depth - 1)
-    if r < 0.25:
-        return f"({a} + {b})"
-    if r < 0.45:
-        return f"({a} - {b})"
-    if r < 0.7:
-        return f"({a})*({b})"
-    if r < 0.88:
-        return f"({a})/({b})"
-    if r < 0.94:
-        return f"sqrt(fabs({a}) + 0.125)"
-    if r < 0.97:
-        return f"sqrt({a})"  # may be NaN: legit
-    return f"pow({a}, 2)"
-
-
-def make_unit(seed: int) -> str:
-    rng = random.Random(seed)
-    xa = "(const double x[], const double args[])"
-    text = PREAMBLE % (N_PAR, seed)
-    for name in ("V", "v00", "v01", "v10", "v11", "grad_norm_squared"):
-        text += f"double {name}{xa}{{\n    return {rand_expr(rng, rng.randint(3, 6))};\n}}\n\n"
-    text += (
-        "double inner_prod(const double x[], const double args[], const double v1[], "
-        "const double v2[]){\n    const double g00 = 1;\n    const double g11 = 1;\n"
-        "    return 0.0 + (g00 * v1[0] * v2[0]) + (g11 * v1[1] * v2[1]);\n}\n\n"
-    )
-    for name in ("v", "w1"):
-        text += (
-            f"void {name}(const double x[], const double args[], double v_out[]){{\n"
-            f"    v_out[0] = {rand_expr(rng, 3)};\n    v_out[1] = {rand_expr(rng, 3)};\n    return;\n}}\n\n"
-        )
-    return text
-
-
-class _RawOracle(oracle.Oracle):
-    """oracle driver over an arbitrary generated C unit (same reference flag set)."""
-
-    def __init__(self, c_text: str, workdir: str):
-        src = os.path.join(workdir, "model.c")
-        so = os.path.join(workdir, "model.so")
-        with open(src, "w") as fh:
-            fh.write(c_text)
-        subprocess.run(
-            ["gcc", "-o", so, src, *[f for f in oracle.REFERENCE_FLAGS if f != "-Werror"],
-             "-ffp-contract=off"], check=True)  # fmt: skip
-        b = oracle._Build()
-        self.quad, self.sfx = False, ""
-        self.lib = ctypes.CDLL(b.driver(False))
-        self.path, self.h = so, ctypes.c_void_p()
-        fn = self.lib.oracle_open
-        fn.restype = ctypes.c_int
-        assert fn(so.encode(), ctypes.byref(self.h)) == 0
-        self.n_fields, self.n_params, self.meta = 2, N_PAR, {}
+from raw_units import N_PAR, PREAMBLE, RawOracle as _RawOracle, make_unit  # noqa: E402
 
 
 def _bit_identical(a, b):
@@ -105,9 +24,9 @@ def _bit_identical(a, b):
     return (a.view(np.uint64) == b.view(np.uint64)) | nan | ((a == 0) & (b == 0))
 
 
-@pytest.mark.parametrize("seed", range(12))
-def test_random_arithmetic_models_are_bit_identical(seed, tmp_path):
-    c_text = make_unit(seed)
+@pytest.mark.parametrize("seed,conditionals", [(k, False) for k in range(12)] + [(k, True) for k in range(100, 110)])
+def test_random_arithmetic_models_are_bit_identical(seed, conditionals, tmp_path):
+    c_text = make_unit(seed, conditionals)
     orc = _RawOracle(c_text, str(tmp_path))
     comp = Compiler.__new__(Compiler)
     comp.nvrtc_opts = list(Compiler.default_nvrtc_flags)
