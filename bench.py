@@ -191,7 +191,8 @@ def config_dict(cfg, model, op, n0, n1, S, gpus):
         "sharding": f"rows/{gpus}" if S < gpus or S == 1 else f"vectors/{gpus}",
         "l2": "outputs per step exceed the 126 MB L2; no flush" if n0 * n1 * S * 48 > (1 << 28)
         else "L2 flushed between timed steps (256 MB memset)",
-        "mode": "strict (--fmad=false, IEEE div/sqrt)",
+        "mode": "fast (--fmad=true)" if os.environ.get("INFLATOX_FMAD", "") not in ("", "0")
+        else "strict (--fmad=false, IEEE div/sqrt)",
     }
 
 
