@@ -5,8 +5,9 @@ python/inflatox/consistency_conditions.py:31-715; every method allocates the num
 `start_stop` and hands the work to `libinflx_rs` (here: the CUDA engine) exactly like the
 reference does with its Rust extension.  The only differences a caller can observe:
 
-  * outputs larger than a few MiB are allocated in pooled page-locked memory so the GPUs DMA
-    straight into the array the caller receives (`INFLATOX_PINNED=0` restores plain np.zeros);
+  * outputs larger than a few MiB come from a host pool: page-locked blocks (the GPUs DMA straight
+    into the array the caller receives) once a background thread has pinned one of that size,
+    pooled pageable blocks until then (`INFLATOX_PINNED=0` restores plain np.zeros);
   * `threads` / `progress` are accepted and ignored (there is no CPU thread pool);
   * `GeneralisedAL.sweep_complete_analysis` is an addition (fused parameter sweep, BASELINE C5).
 """
@@ -29,7 +30,7 @@ def _new_output(shape, dtype=float) -> np.ndarray:
     """np.zeros for the caller-visible result; pinned (pooled) when large enough to matter."""
     nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
     if nbytes >= _PIN_THRESHOLD and os.environ.get("INFLATOX_PINNED", "1") != "0":
-        return _rs.pinned_empty(shape, dtype)
+        return _rs.host_output(shape, dtype)
     return np.zeros(shape, dtype=dtype)
 
 

@@ -23,6 +23,8 @@
 #include <thread>
 #include <vector>
 
+#include <sys/mman.h>
+
 #if defined(__x86_64__)
 #include <immintrin.h>
 #endif
@@ -172,6 +174,9 @@ static inflx_status ensure_pin(CudaDriver& cu, PinBuf& b, size_t bytes) {
   b.cap = bytes;
   return INFLX_OK;
 }
+
+static std::mutex g_host_mu;
+static std::map<void*, size_t> g_host_maps;  // inflx_host_alloc blocks that are registered mmaps
 
 static std::mutex g_dev_mu;
 static std::map<int, std::unique_ptr<DeviceState>> g_devices;
@@ -1243,15 +1248,48 @@ inflx_status inflx_measure_fp64_peak(int device, int repeats, double* tflops_bes
 }
 
 // ---- pinned host memory ------------------------------------------------------------------------
+// Large blocks: anonymous mmap + MADV_HUGEPAGE, pre-faulted by a few threads, then registered with
+// the driver.  Measured on the round-1 box for 12 GiB (tools/pin_probe.py): cuMemHostAlloc 5.7 s
+// (and it holds the driver's lock for all of it, stalling every concurrent launch/copy);
+// populate 1.3-1.4 s (no driver involvement) + cuMemHostRegister 1.0-2.3 s; same 55 GB/s D2H rate.
 inflx_status inflx_host_alloc(size_t bytes, void** ptr) {
   *ptr = nullptr;
   CudaDriver& cu = CudaDriver::get();
   if (!cu.ok) return fail(INFLX_ERR_CUDA, cu.error);
-  DeviceState* dev = nullptr;  // a context must be current for cuMemHostAlloc
+  DeviceState* dev = nullptr;  // a context must be current for cuMemHostAlloc / cuMemHostRegister
   std::vector<int> d = default_devices();
   inflx_status st = get_device(d.empty() ? 0 : d[0], &dev);
   if (st) return st;
   CU_TRY(cu.p_cuCtxSetCurrent(dev->ctx));
+  const char* mode = getenv("INFLATOX_HOST_ALLOC");
+  const bool want_mmap = bytes >= (size_t(64) << 20) && !(mode && !strcmp(mode, "cuda"));
+  if (want_mmap) {
+    const size_t huge = size_t(2) << 20, len = (bytes + huge - 1) & ~(huge - 1);
+    void* m = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (m != MAP_FAILED) {
+      madvise(m, len, MADV_HUGEPAGE);
+      const unsigned nt = std::max(1u, std::min(4u, std::thread::hardware_concurrency()));
+      const size_t per = ((len / nt) + huge - 1) & ~(huge - 1);
+      std::vector<std::thread> th;
+      for (unsigned k = 0; k < nt; ++k) {
+        const size_t lo = std::min(len, k * per), hi = std::min(len, lo + per);
+        if (lo < hi)
+          th.emplace_back([=] {
+            char* q = static_cast<char*>(m);
+            if (madvise(q + lo, hi - lo, 23 /* MADV_POPULATE_WRITE */) != 0)
+              for (size_t o = lo; o < hi; o += 4096) q[o] = 0;
+          });
+      }
+      for (auto& t : th) t.join();
+      if (cu.p_cuMemHostRegister(m, len, CU_MEMHOSTREGISTER_PORTABLE) == CUDA_SUCCESS) {
+        std::lock_guard<std::mutex> lk(g_host_mu);
+        g_host_maps[m] = len;
+        *ptr = m;
+        return INFLX_OK;
+      }
+      munmap(m, len);  // fall through to the driver's own allocator
+    }
+  }
   CU_TRY(cu.p_cuMemHostAlloc(ptr, bytes ? bytes : 1, CU_MEMHOSTALLOC_PORTABLE));
   return INFLX_OK;
 }
@@ -1259,6 +1297,21 @@ inflx_status inflx_host_free(void* ptr) {
   if (!ptr) return INFLX_OK;
   CudaDriver& cu = CudaDriver::get();
   if (!cu.ok) return fail(INFLX_ERR_CUDA, cu.error);
+  size_t len = 0;
+  {
+    std::lock_guard<std::mutex> lk(g_host_mu);
+    auto it = g_host_maps.find(ptr);
+    if (it != g_host_maps.end()) {
+      len = it->second;
+      g_host_maps.erase(it);
+    }
+  }
+  if (len) {
+    CUresult r = cu.p_cuMemHostUnregister(ptr);
+    munmap(ptr, len);
+    CU_TRY(r);
+    return INFLX_OK;
+  }
   CU_TRY(cu.p_cuMemFreeHost(ptr));
   return INFLX_OK;
 }

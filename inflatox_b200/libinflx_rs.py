@@ -11,7 +11,10 @@ NotImplementedError.
 from __future__ import annotations
 
 import ctypes
+import mmap
+import os
 import sys
+import threading
 
 import numpy as np
 
@@ -22,7 +25,7 @@ __all__ = [
     "consistency_only", "consistency_rapidturn_only", "epsilon_v_only", "complete_analysis",
     "complete_analysis_on_trajectory", "consistency_only_on_trajectory",
     "consistency_rapidturn_only_on_trajectory", "epsilon_v_only_on_trajectory", "solve_eom_rk4",
-    "solve_eom_rkf", "PanicException", "pinned_empty", "sweep", "grid_eval",
+    "solve_eom_rkf", "PanicException", "pinned_empty", "host_output", "sweep", "grid_eval",
 ]  # fmt: skip
 
 _DP = ctypes.POINTER(ctypes.c_double)
@@ -296,52 +299,143 @@ solve_eom_rkf = solve_eom_rk4
 class _PinnedBlock:
     """Owner of one cuMemHostAlloc block; freed when the last numpy view dies."""
 
+    pinned = True
+
+    total = 0  # bytes currently page-locked through this pool
+
     def __init__(self, nbytes: int):
         ptr = ctypes.c_void_p()
         _native.raise_for_status(_native.lib().inflx_host_alloc(nbytes, ctypes.byref(ptr)))
         self.ptr, self.nbytes = ptr, nbytes
+        _PinnedBlock.total += nbytes
+
+    def address(self) -> int:
+        return self.ptr.value
 
     def __del__(self):
         p, self.ptr = getattr(self, "ptr", None), None
         if p:
             try:
                 _native.lib().inflx_host_free(p)
+                _PinnedBlock.total -= self.nbytes
             except Exception:
                 pass
 
 
+class _PageableBlock:
+    """Plain (pageable) host block: an anonymous mapping backed by transparent huge pages where the
+    kernel offers them (first-touch faults cost half of what 4 KiB pages do), reused so that the
+    pages are faulted in only once."""
+
+    pinned = False
+
+    def __init__(self, nbytes: int):
+        self.map = mmap.mmap(-1, nbytes)
+        try:
+            self.map.madvise(mmap.MADV_HUGEPAGE)
+        except (AttributeError, OSError, ValueError):
+            pass
+        self.view = np.frombuffer(self.map, dtype=np.uint8)
+        self.nbytes = nbytes
+
+    def address(self) -> int:
+        return self.view.ctypes.data
+
+
+_pool_lock = threading.Lock()
 _pin_pool: dict[int, list[_PinnedBlock]] = {}
+_page_pool: dict[int, list[_PageableBlock]] = {}
+_pin_jobs: dict[int, threading.Thread] = {}
+_POOL_DEPTH = 4
 
 
-class _PinnedLease:
-    """Returns the block to the pool (instead of unpinning it) when the array is collected."""
+class _Lease:
+    """Returns a block to its pool (instead of freeing / unpinning it) when the array dies."""
 
-    def __init__(self, block: _PinnedBlock):
+    def __init__(self, block):
         self.block = block
 
     def __del__(self):
         try:
-            pool = _pin_pool.setdefault(self.block.nbytes, [])
-            if len(pool) < 4:
-                pool.append(self.block)
+            pools = _pin_pool if self.block.pinned else _page_pool
+            with _pool_lock:
+                pool = pools.setdefault(self.block.nbytes, [])
+                if len(pool) < _POOL_DEPTH:
+                    pool.append(self.block)
         except Exception:  # interpreter shutdown: module globals may already be gone
             pass
 
 
-def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
-    """numpy array in page-locked host memory (pooled: pinning costs more than the kernels).
-    Outputs allocated here are written by DMA straight from the GPU(s)."""
+def _pin_budget() -> int:
+    """Upper bound on page-locked pool memory: $INFLATOX_PINNED_MAX_GB, else a third of the RAM."""
+    env = os.environ.get("INFLATOX_PINNED_MAX_GB")
+    if env:
+        return int(float(env) * (1 << 30))
+    try:
+        return os.sysconf("SC_PAGE_SIZE") * os.sysconf("SC_PHYS_PAGES") // 3
+    except (ValueError, OSError):
+        return 16 << 30
+
+
+def _round_block(shape, dtype) -> tuple[tuple, int, int]:
     shape = tuple(int(s) for s in (shape if hasattr(shape, "__len__") else (shape,)))
-    nbytes = max(1, int(np.prod(shape)) * np.dtype(dtype).itemsize)
-    nbytes = (nbytes + (1 << 21) - 1) & ~((1 << 21) - 1)
-    pool = _pin_pool.get(nbytes)
-    block = pool.pop() if pool else _PinnedBlock(nbytes)
-    lease = _PinnedLease(block)
-    buf = (ctypes.c_char * nbytes).from_address(block.ptr.value)
-    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
-    # keep the lease alive as long as any view of the buffer exists
-    buf._inflx_lease = lease
+    count = int(np.prod(shape))
+    nbytes = max(1, count * np.dtype(dtype).itemsize)
+    return shape, count, (nbytes + (1 << 21) - 1) & ~((1 << 21) - 1)
+
+
+def _as_array(block, shape, count, dtype) -> np.ndarray:
+    lease = _Lease(block)
+    buf = (ctypes.c_char * block.nbytes).from_address(block.address())
+    arr = np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+    buf._inflx_lease = lease  # keep the lease alive as long as any view of the buffer exists
     return arr
+
+
+def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
+    """numpy array in page-locked host memory, allocated NOW (pinning runs at ~2.5 GB/s, so this
+    blocks for seconds on a multi-GB array) and pooled.  Outputs allocated here are written by DMA
+    straight from the GPU(s)."""
+    shape, count, nbytes = _round_block(shape, dtype)
+    with _pool_lock:
+        pool = _pin_pool.get(nbytes)
+        block = pool.pop() if pool else None
+    if block is None:
+        block = _PinnedBlock(nbytes)
+    return _as_array(block, shape, count, dtype)
+
+
+def host_output(shape, dtype=np.float64) -> np.ndarray:
+    """Output array for the facade.  A pinned block from the pool when one is free (direct DMA,
+    ~55 GB/s); otherwise a pooled pageable block for THIS call (staged copy-out, 30-47 GB/s) while
+    a background thread page-locks a block of that size for the next ones, so that a cold call
+    does not wait the seconds it takes to pin its own output first."""
+    shape, count, nbytes = _round_block(shape, dtype)
+    with _pool_lock:
+        pool = _pin_pool.get(nbytes)
+        block = pool.pop() if pool else None
+        if block is None:
+            job = _pin_jobs.get(nbytes)
+            if (job is None or not job.is_alive()) and _PinnedBlock.total + nbytes <= _pin_budget():
+
+                def pin(nb=nbytes):
+                    try:
+                        blk = _PinnedBlock(nb)
+                    except Exception:
+                        return  # no GPU / out of lockable memory: stay on the staged path
+                    with _pool_lock:
+                        _pin_pool.setdefault(nb, []).append(blk)
+
+                # not a daemon: interpreter shutdown waits for a page-lock in flight instead of
+                # tearing the driver down under it
+                job = threading.Thread(target=pin, daemon=False)
+                _pin_jobs[nbytes] = job
+                job.start()
+            pages = _page_pool.get(nbytes)
+            block = pages.pop() if pages else None
+    if block is None:
+        block = _PageableBlock(nbytes)
+    return _as_array(block, shape, count, dtype)
 
 
 def grid_eval(lib, op: str, p, out, n0: int, n1: int, start_stop, rows=None, accuracy: float = 0.0,
