@@ -1267,6 +1267,8 @@ inflx_status inflx_host_alloc(size_t bytes, void** ptr) {
     const size_t huge = size_t(2) << 20, len = (bytes + huge - 1) & ~(huge - 1);
     void* m = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
     if (m != MAP_FAILED) {
+      const bool dbg = getenv("INFLATOX_DEBUG_POOL") != nullptr;
+      const auto t0 = std::chrono::steady_clock::now();
       madvise(m, len, MADV_HUGEPAGE);
       const unsigned nt = std::max(1u, std::min(4u, std::thread::hardware_concurrency()));
       const size_t per = ((len / nt) + huge - 1) & ~(huge - 1);
@@ -1281,7 +1283,15 @@ inflx_status inflx_host_alloc(size_t bytes, void** ptr) {
           });
       }
       for (auto& t : th) t.join();
-      if (cu.p_cuMemHostRegister(m, len, CU_MEMHOSTREGISTER_PORTABLE) == CUDA_SUCCESS) {
+      const auto t1 = std::chrono::steady_clock::now();
+      const CUresult reg = cu.p_cuMemHostRegister(m, len, CU_MEMHOSTREGISTER_PORTABLE);
+      if (dbg)
+        fprintf(stderr, "[inflx_host_alloc] %zu MiB: populate %.0f ms, register %.0f ms (rc %d)\n",
+                len >> 20, std::chrono::duration<double, std::milli>(t1 - t0).count(),
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1)
+                    .count(),
+                (int)reg);
+      if (reg == CUDA_SUCCESS) {
         std::lock_guard<std::mutex> lk(g_host_mu);
         g_host_maps[m] = len;
         *ptr = m;

@@ -326,6 +326,8 @@ class GroupProgram:
             rcp = self.rcp_of[n[2]]
             fn = "inflx_div_yh" if self.klass(rcp) != self.klass(i) else "inflx_div_y"
             y = self._ref(rcp, scope)
+            if d.is_const(n[1]) and float(d.cval(n[1])) == 1.0:  # 1.0 / b: one DMUL less
+                return f"{fn.replace('div', 'inv')}({self._ref(n[2], scope)}, {y}, bad)"
             return f"{fn}({self._ref(n[1], scope)}, {self._ref(n[2], scope)}, {y}, bad)"
         if k in ("+", "-", "*", "/"):
             return f"{self._ref(n[1], scope)} {k} {self._ref(n[2], scope)}"

@@ -11,10 +11,10 @@ NotImplementedError.
 from __future__ import annotations
 
 import ctypes
-import mmap
 import os
 import sys
 import threading
+import time
 
 import numpy as np
 
@@ -68,6 +68,48 @@ def _out(a, dtype, what: str) -> np.ndarray:
 
 def _dptr(a: np.ndarray):
     return a.ctypes.data_as(_DP)
+
+
+class _EngineGate:
+    """Counts engine calls in flight.  Page-locking a multi-GB block holds the CUDA driver's lock
+    for seconds, so the background pin jobs of the output pool (below) wait here until the
+    engine is idle instead of stalling the very call they were started from."""
+
+    def __init__(self):
+        self.cond = threading.Condition()
+        self.busy = 0
+        self.completed = 0
+        self.closing = False
+
+    def __enter__(self):
+        with self.cond:
+            self.busy += 1
+
+    def __exit__(self, *exc):
+        with self.cond:
+            self.busy -= 1
+            self.completed += 1
+            self.cond.notify_all()
+
+    def wait_idle_after(self, completed: int, timeout: float) -> None:
+        """Block until a call newer than `completed` has finished and none is running (or until
+        `timeout` seconds have passed: the caller may never use the array it asked for)."""
+        with self.cond:
+            self.cond.wait_for(
+                lambda: self.closing or (self.busy == 0 and self.completed > completed), timeout
+            )
+
+    def close(self) -> None:
+        with self.cond:
+            self.closing = True
+            self.cond.notify_all()
+
+
+_gate = _EngineGate()
+try:  # wake waiting pin jobs when the interpreter starts to shut down (before threads are joined)
+    threading._register_atexit(_gate.close)
+except Exception:  # private hook missing: the jobs' own timeout bounds the wait
+    pass
 
 
 def _ss(start_stop) -> np.ndarray:
@@ -147,10 +189,11 @@ class InflatoxPyDyLib:
                 "Context: expected an array with with the same number of axes as there are "
                 "field-space coordinates"
             )
-        rc = _native.lib().inflx_potential_array(
-            self._h, _dptr(x), x.shape[0], x.shape[1], _dptr(p), p.size, _dptr(ss), ss.shape[0],
-            ss.shape[1],
-        )  # fmt: skip
+        with _gate:
+            rc = _native.lib().inflx_potential_array(
+                self._h, _dptr(x), x.shape[0], x.shape[1], _dptr(p), p.size, _dptr(ss),
+                ss.shape[0], ss.shape[1],
+            )  # fmt: skip
         _native.raise_for_status(rc)
 
     def hesse(self, x, p) -> np.ndarray:
@@ -170,10 +213,11 @@ class InflatoxPyDyLib:
                 "field-space coordinates"
             )
         out = np.zeros((2, 2, int(nx[0]), int(nx[1])), dtype=np.float64)
-        rc = _native.lib().inflx_hesse_array(
-            self._h, _dptr(out), int(nx[0]), int(nx[1]), _dptr(p), p.size, _dptr(ss), ss.shape[0],
-            ss.shape[1],
-        )  # fmt: skip
+        with _gate:
+            rc = _native.lib().inflx_hesse_array(
+                self._h, _dptr(out), int(nx[0]), int(nx[1]), _dptr(p), p.size, _dptr(ss),
+                ss.shape[0], ss.shape[1],
+            )  # fmt: skip
         _native.raise_for_status(rc)
         return out
 
@@ -194,10 +238,11 @@ def _grid2(fn_name: str, lib, p, out, start_stop, progress, threads) -> None:
     out = _out(out, np.float64, "out")
     if out.ndim != 2:
         raise TypeError("out must be a 2D float64 array")
-    rc = getattr(_native.lib(), fn_name)(
-        lib._h, _dptr(p), p.size, _dptr(out), out.shape[0], out.shape[1], _dptr(ss), ss.shape[0],
-        ss.shape[1], int(bool(progress)), int(threads),
-    )  # fmt: skip
+    with _gate:
+        rc = getattr(_native.lib(), fn_name)(
+            lib._h, _dptr(p), p.size, _dptr(out), out.shape[0], out.shape[1], _dptr(ss),
+            ss.shape[0], ss.shape[1], int(bool(progress)), int(threads),
+        )  # fmt: skip
     _native.raise_for_status(rc)
 
 
@@ -218,10 +263,11 @@ def complete_analysis(lib, p, out, start_stop, progress, threads) -> None:
     out = _out(out, np.float64, "out")
     if out.ndim != 3:
         raise TypeError("out must be a 3D float64 array")
-    rc = _native.lib().inflx_complete_analysis(
-        lib._h, _dptr(p), p.size, _dptr(out), out.shape[0], out.shape[1], out.shape[2], _dptr(ss),
-        ss.shape[0], ss.shape[1], int(bool(progress)), int(threads),
-    )  # fmt: skip
+    with _gate:
+        rc = _native.lib().inflx_complete_analysis(
+            lib._h, _dptr(p), p.size, _dptr(out), out.shape[0], out.shape[1], out.shape[2],
+            _dptr(ss), ss.shape[0], ss.shape[1], int(bool(progress)), int(threads),
+        )  # fmt: skip
     _native.raise_for_status(rc)
 
 
@@ -230,10 +276,11 @@ def flag_quantum_dif_py(lib, p, x, start_stop, progress, accuracy) -> None:
     x = _out(x, np.bool_, "x")
     if x.ndim != 2:
         raise TypeError("x must be a 2D bool array")
-    rc = _native.lib().inflx_flag_quantum_dif(
-        lib._h, _dptr(p), p.size, x.ctypes.data_as(ctypes.c_void_p), x.shape[0], x.shape[1],
-        _dptr(ss), ss.shape[0], ss.shape[1], int(bool(progress)), float(accuracy),
-    )  # fmt: skip
+    with _gate:
+        rc = _native.lib().inflx_flag_quantum_dif(
+            lib._h, _dptr(p), p.size, x.ctypes.data_as(ctypes.c_void_p), x.shape[0], x.shape[1],
+            _dptr(ss), ss.shape[0], ss.shape[1], int(bool(progress)), float(accuracy),
+        )  # fmt: skip
     _native.raise_for_status(rc)
 
 
@@ -323,23 +370,19 @@ class _PinnedBlock:
 
 
 class _PageableBlock:
-    """Plain (pageable) host block: an anonymous mapping backed by transparent huge pages where the
-    kernel offers them (first-touch faults cost half of what 4 KiB pages do), reused so that the
-    pages are faulted in only once."""
+    """Plain (pageable) host block; reused so that its pages are faulted in only once.  Ordinary
+    4 KiB pages on purpose: the copy-out threads fault them in in parallel at memcpy speed,
+    whereas first-touching a MADV_HUGEPAGE mapping from those threads cost 2-6 s per 12 GiB on the
+    round-1 boxes (tools/coldstart_probe.py)."""
 
     pinned = False
 
     def __init__(self, nbytes: int):
-        self.map = mmap.mmap(-1, nbytes)
-        try:
-            self.map.madvise(mmap.MADV_HUGEPAGE)
-        except (AttributeError, OSError, ValueError):
-            pass
-        self.view = np.frombuffer(self.map, dtype=np.uint8)
+        self.buf = np.empty(nbytes + 64, dtype=np.uint8)
         self.nbytes = nbytes
 
     def address(self) -> int:
-        return self.view.ctypes.data
+        return (self.buf.ctypes.data + 63) & ~63
 
 
 _pool_lock = threading.Lock()
@@ -405,24 +448,46 @@ def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
     return _as_array(block, shape, count, dtype)
 
 
+def _pool_debug(msg: str) -> None:
+    if os.environ.get("INFLATOX_DEBUG_POOL"):
+        print(f"[inflatox pool {time.perf_counter():.3f}] {msg}", file=sys.stderr, flush=True)
+
+
 def host_output(shape, dtype=np.float64) -> np.ndarray:
     """Output array for the facade.  A pinned block from the pool when one is free (direct DMA,
     ~55 GB/s); otherwise a pooled pageable block for THIS call (staged copy-out, 30-47 GB/s) while
     a background thread page-locks a block of that size for the next ones, so that a cold call
-    does not wait the seconds it takes to pin its own output first."""
+    does not wait the seconds it takes to pin its own output first.  Page-locking holds the
+    driver's lock, so the job waits until the engine call this array is for has returned
+    ($INFLATOX_PIN_MODE: `deferred` (default) | `eager`: pin concurrently | `sync`: pin in the
+    call, the pre-pool behaviour | `off`: pageable only)."""
+    mode = os.environ.get("INFLATOX_PIN_MODE", "deferred")
+    if mode == "sync":
+        return pinned_empty(shape, dtype)
     shape, count, nbytes = _round_block(shape, dtype)
     with _pool_lock:
         pool = _pin_pool.get(nbytes)
         block = pool.pop() if pool else None
         if block is None:
             job = _pin_jobs.get(nbytes)
-            if (job is None or not job.is_alive()) and _PinnedBlock.total + nbytes <= _pin_budget():
+            if (
+                mode != "off"
+                and (job is None or not job.is_alive())
+                and _PinnedBlock.total + nbytes <= _pin_budget()
+            ):
+                seen = _gate.completed
 
                 def pin(nb=nbytes):
+                    if mode != "eager":
+                        _gate.wait_idle_after(seen, timeout=10.0)
+                    if _gate.closing:
+                        return
+                    _pool_debug(f"pinning {nb >> 20} MiB")
                     try:
                         blk = _PinnedBlock(nb)
                     except Exception:
                         return  # no GPU / out of lockable memory: stay on the staged path
+                    _pool_debug(f"pinned {nb >> 20} MiB")
                     with _pool_lock:
                         _pin_pool.setdefault(nb, []).append(blk)
 
@@ -435,6 +500,7 @@ def host_output(shape, dtype=np.float64) -> np.ndarray:
             block = pages.pop() if pages else None
     if block is None:
         block = _PageableBlock(nbytes)
+    _pool_debug(f"output {nbytes >> 20} MiB: {'pinned' if block.pinned else 'pageable'}")
     return _as_array(block, shape, count, dtype)
 
 
@@ -473,9 +539,9 @@ def grid_eval(lib, op: str, p, out, n0: int, n1: int, start_stop, rows=None, acc
         rq.out_is_device = 0
     rq.device = device
     rep = _native.GridReport()
-    _native.raise_for_status(
-        _native.lib().inflx_grid_eval(lib._h, ctypes.byref(rq), ctypes.byref(rep))
-    )
+    with _gate:
+        rc = _native.lib().inflx_grid_eval(lib._h, ctypes.byref(rq), ctypes.byref(rep))
+    _native.raise_for_status(rc)
     return {
         "kernel_ms": rep.kernel_ms, "grid_ms": rep.grid_ms, "total_ms": rep.total_ms, "launches": int(rep.launches),
         "d2h_bytes": int(rep.d2h_bytes), "h2d_bytes": int(rep.h2d_bytes),

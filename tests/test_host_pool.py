@@ -7,9 +7,16 @@ import gc
 import time
 
 import numpy as np
+import pytest
 
 from inflatox_b200 import consistency_conditions as cc
 from inflatox_b200 import libinflx_rs as rs
+
+
+@pytest.fixture(autouse=True)
+def _eager_pin_jobs(monkeypatch):
+    # the default mode parks the pin job until an engine call has completed; there is none here
+    monkeypatch.setenv("INFLATOX_PIN_MODE", "eager")
 
 
 def _wait_jobs():
@@ -73,3 +80,22 @@ def test_pin_budget_env(monkeypatch):
     assert rs._pin_budget() == 1 << 29
     monkeypatch.delenv("INFLATOX_PINNED_MAX_GB")
     assert rs._pin_budget() > 0
+
+
+def test_deferred_pin_job_waits_for_an_engine_call(monkeypatch):
+    monkeypatch.setenv("INFLATOX_PIN_MODE", "deferred")
+    a = rs.host_output((1 << 19, 3))
+    job = rs._pin_jobs[rs._round_block((1 << 19, 3), np.float64)[2]]
+    time.sleep(0.2)
+    assert job.is_alive(), "the job must wait until the call the array is for has returned"
+    with rs._gate:  # stands in for the engine call
+        a[:] = 1.0
+    job.join(timeout=30)
+    assert not job.is_alive()
+
+
+def test_pin_modes(monkeypatch):
+    monkeypatch.setenv("INFLATOX_PIN_MODE", "off")
+    before = dict(rs._pin_jobs)
+    a = rs.host_output((1 << 18, 5))
+    assert rs._pin_jobs == before and a.flags.writeable

@@ -1,4 +1,5 @@
-"""Diagnostic: cold-start cost of one facade call (pinned pool allocation vs staged pageable output)."""
+"""Diagnostic: cold-start cost of the facade's first calls under each output-pool mode
+(INFLATOX_PIN_MODE = deferred | eager | sync | off).  Usage: coldstart_probe.py [n] [pause_s]"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -7,17 +8,22 @@ os.environ.setdefault("INFLATOX_QUIET", "1")
 import numpy as np
 t0 = time.perf_counter()
 import cases
-from inflatox_b200.consistency_conditions import GeneralisedAL
+from inflatox_b200.consistency_conditions import GeneralisedAL, InflationCondition
 art = cases.artifact("egno")
 t1 = time.perf_counter()
-al = GeneralisedAL(art)
+al = GeneralisedAL.__new__(GeneralisedAL)
+InflationCondition.__init__(al, art, validate_basis=False)
 t2 = time.perf_counter()
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
+pause = float(sys.argv[2]) if len(sys.argv) > 2 else 0.0
 p, ext = cases.params("egno"), cases.EXTENT["egno"]
-for k in range(3):
+mode = os.environ.get("INFLATOX_PIN_MODE", "deferred")
+tb = time.perf_counter()
+for k in range(4):
     t = time.perf_counter()
     out = al.complete_analysis(p, *ext, n, n)
     dt = time.perf_counter() - t
-    print(f"PINNED={os.environ.get('INFLATOX_PINNED', '1')} call {k}: {dt * 1e3:.0f} ms ({n * n / dt:.3e} points/s)", flush=True)
+    print(f"mode={mode} pause={pause} call {k}: {dt * 1e3:.0f} ms ({n * n / dt:.3e} points/s)", flush=True)
     del out
-print(f"import+compile {t1 - t0:.2f} s, open+basis check {t2 - t1:.2f} s")
+    time.sleep(pause)
+print(f"mode={mode}: 4 calls + pauses {time.perf_counter() - tb:.2f} s; import+compile {t1 - t0:.2f} s, open {t2 - t1:.2f} s", flush=True)
