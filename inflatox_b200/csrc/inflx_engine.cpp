@@ -116,6 +116,7 @@ static_assert(sizeof(FileHeader) == 192, "container header layout");
 static_assert(sizeof(GroupEntry) == 32, "container group layout");
 
 static const uint16_t kAbi[3] = {5, 0, 0};  // V_INFLX_ABI, reference src/lib.rs:50
+static const uint32_t kContainerVersion = 2;  // inflatox_b200/version.py __container_version__
 static const uint32_t kPcCapacity = 7680;   // doubles, must match cudagen.PC_CAPACITY
 
 struct OpInfo {
@@ -153,6 +154,7 @@ struct DeviceState {
   DevBuf d_p, d_pc, d_rc, d_xs, d_out[2];
   PinBuf stage[2];
   std::string name;
+  int sm_count = 148;
 };
 
 static inflx_status ensure_dev(CudaDriver& cu, DevBuf& b, size_t bytes) {
@@ -200,6 +202,8 @@ static inflx_status get_device(int ordinal, DeviceState** out) {
   char nm[128] = {0};
   cu.p_cuDeviceGetName(nm, sizeof nm, d->dev);
   d->name = nm;
+  cu.p_cuDeviceGetAttribute(&d->sm_count, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, d->dev);
+  if (d->sm_count <= 0) d->sm_count = 148;
   CU_TRY(cu.p_cuDevicePrimaryCtxRetain(&d->ctx, d->dev));
   CU_TRY(cu.p_cuCtxSetCurrent(d->ctx));
   CU_TRY(cu.p_cuStreamCreate(&d->compute, CU_STREAM_NON_BLOCKING));
@@ -571,9 +575,26 @@ static inflx_status run_shard(inflx_lib* lib, const inflx_grid_request& rq, cons
       }
       double aux = rq.aux;
       if (k == 0) CU_TRY(cu.p_cuEventRecord(dev->ev_g0, cs));
-      void* args[] = {&outp, &dev->d_rc.ptr, &of1, &dx1, &n1u, &n_rows, &comp_stride, &aux};
-      if ((st = launch(cu, grid_fn, (unsigned)((n1 + BLOCK - 1) / BLOCK),
-                       (unsigned)((rc + RPT - 1) / RPT), (unsigned)sc, BLOCK, cs, args)))
+      // rows per CTA (tools/tune.py sweeps, profiles/tune_rpt_r1.log): the artefact's maximum (16)
+      // when that still leaves ~16 waves of CTAs - the column block and the smem staging then
+      // amortise over more rows (16384^2 grids: hyper +5.5 %, angular +1.6 %, d5 +1 %, EGNO +-0
+      // against 8 rows); else the largest of 8/4/2 that leaves ~4 waves (4096^2: 8 rows are 3 %
+      // faster than 16; 1000^2-2048^2: 2-4 rows are 5-30 % faster than 8 on all but the cheapest
+      // model, whose 20 us launch does not care).
+      const uint64_t col_tiles = (n1 + BLOCK - 1) / BLOCK;
+      uint32_t rpt = RPT;
+      if (const char* e = getenv("INFLATOX_RPT")) {
+        rpt = (uint32_t)std::min<long>(std::max<long>(atol(e), 1), RPT);
+      } else {
+        const uint64_t wave = (uint64_t)dev->sm_count * 8;
+        auto ctas = [&](uint32_t r) { return col_tiles * ((rc + r - 1) / r) * sc; };
+        if (rpt > 8 && ctas(rpt) < 16 * wave) rpt = 8;
+        while (rpt > 2 && ctas(rpt) < 4 * wave) rpt /= 2;
+      }
+      while (rpt < RPT && (rc + rpt - 1) / rpt > 65535) rpt *= 2;  // gridDim.y limit
+      void* args[] = {&outp, &dev->d_rc.ptr, &of1, &dx1, &n1u, &n_rows, &comp_stride, &aux, &rpt};
+      if ((st = launch(cu, grid_fn, (unsigned)col_tiles, (unsigned)((rc + rpt - 1) / rpt),
+                       (unsigned)sc, BLOCK, cs, args)))
         return st;
       res.launches++;
       if (to_device) CU_TRY(cu.p_cuEventRecord(dev->ev_g1, cs));
@@ -701,6 +722,11 @@ inflx_status inflx_open(const char* lib_path, int check_basis, inflx_lib** out) 
                 fmt("Cannot load Inflatox Compilation Artefact compiled for Inflatox ABI v%u.%u.%u "
                     "using current Inflatox installation (v%u.%u.%u)", h.abi[0], h.abi[1], h.abi[2],
                     kAbi[0], kAbi[1], kAbi[2]));
+  if (h.container_version != kContainerVersion)
+    return fail(INFLX_ERR_VERSION,
+                fmt("Cannot load Inflatox Compilation Artefact with container layout v%u using "
+                    "current Inflatox installation (container layout v%u): compile the model again",
+                    h.container_version, kContainerVersion));
   if (sizeof(FileHeader) + (size_t)h.n_groups * sizeof(GroupEntry) > lib->file.size())
     return fail(INFLX_ERR_IO, fmt("Could not load Inflatox Compilation Artefact (path: %s). "
                                   "Error: \"truncated artefact\"", lib_path));

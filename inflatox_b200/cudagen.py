@@ -569,15 +569,16 @@ class GroupProgram:
         return (
             f"extern \"C\" __global__ void __launch_bounds__(INFLX_BLOCK, INFLX_MIN_BLOCKS) {name}("
             "double* __restrict__ out, const double* __restrict__ rc, double of1, double dx1, "
-            "u32 n1, u32 n_rows, u64 comp_stride, double aux) {\n"
+            "u32 n1, u32 n_rows, u64 comp_stride, double aux, u32 rpt) {\n"
             "  const u32 col = blockIdx.x * INFLX_BLOCK + threadIdx.x;\n"
             + (
                 "  const u32 s = blockIdx.z;\n  const u32 pbase = s * INFLX_NPF;\n"
                 if sweep
                 else "  const u32 s = 0;\n  const u32 pbase = 0;\n"
             )
-            + "  const u32 r0 = blockIdx.y * INFLX_RPT;\n"
-            "  const u32 rows_here = min((u32)INFLX_RPT, n_rows - r0);\n"
+            # rows per CTA: chosen per launch by the engine (<= INFLX_RPT, which sizes the smem)
+            + "  const u32 r0 = blockIdx.y * rpt;\n"
+            "  const u32 rows_here = min(rpt, n_rows - r0);\n"
             # the CTA's rows of the row-frontier array: one cooperative, coalesced 128-bit copy
             # into shared memory, overlapped with the column block; per-point reads are then
             # conflict-free LDS.128 broadcasts instead of exposed L2 round trips

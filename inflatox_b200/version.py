@@ -9,4 +9,4 @@ in their `VERSION` global and `inflx_open` refuses an artefact whose major.minor
 __version__ = "0.1.0"
 __abi_version__ = "5.0.0"
 # Version of the *container* this package wraps around the cubin (see compiler.py / inflx_b200.h)
-__container_version__ = 1
+__container_version__ = 2  # 2: grid kernels take the rows-per-CTA count as a launch argument

@@ -54,6 +54,12 @@ def test_open_errors_mirror_the_reference(tmp_path):
     ok = tmp_path / "patch.bin"
     ok.write_bytes(bytes(blob))
     assert rs.open_inflx_dylib(str(ok), False).n_fields == 2
+    # container layout: an artefact of an older kernel ABI must be refused, not launched
+    blob[8:12] = (1).to_bytes(4, "little")
+    stale = tmp_path / "stale.bin"
+    stale.write_bytes(bytes(blob))
+    with pytest.raises(SystemError, match="container layout v1"):
+        rs.open_inflx_dylib(str(stale), False)
 
 
 def test_handle_metadata():

@@ -42,6 +42,10 @@ def main():
         except Exception as e:
             print(v, "compile failed", str(e)[:200])
             continue
+        if "run_rpt" in v:  # rows per CTA the engine uses at launch time (<= the compiled maximum)
+            os.environ["INFLATOX_RPT"] = str(v["run_rpt"])
+        else:
+            os.environ.pop("INFLATOX_RPT", None)
         lib = rs.open_inflx_dylib(art.shared_object_path, False)
         lib.set_devices([0])
         ts = []
