@@ -107,7 +107,8 @@ struct FileHeader {
   uint32_t pad;
 };
 struct GroupEntry {
-  char name[8];
+  char name[4];
+  uint32_t ncf;  // column-frontier values per column (0: the column block runs inside the grid kernel)
   uint32_t npf, nrf;
   uint64_t cubin_offset, cubin_size;
 };
@@ -151,7 +152,7 @@ struct DeviceState {
   CUevent ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
   CUevent ev_t0 = nullptr, ev_t1 = nullptr, ev_g0 = nullptr, ev_g1 = nullptr;
   std::mutex mu;  // one grid call at a time per device (scratch buffers are shared)
-  DevBuf d_p, d_pc, d_rc, d_xs, d_out[2];
+  DevBuf d_p, d_pc, d_rc, d_cc, d_xs, d_out[2];
   PinBuf stage[2];
   std::string name;
   int sm_count = 148;
@@ -289,7 +290,7 @@ using namespace inflx;
 struct GroupModule {
   CUmodule mod = nullptr;
   CUdeviceptr pc_sym = 0;
-  CUfunction params = nullptr, rows = nullptr;
+  CUfunction params = nullptr, rows = nullptr, cols = nullptr;
   std::map<std::string, CUfunction> fns;
 };
 
@@ -330,6 +331,7 @@ static inflx_status load_module(inflx_lib* lib, DeviceState* dev, const char* gr
   CU_TRY(cu.p_cuModuleGetGlobal(&gm->pc_sym, &bytes, gm->mod, "inflx_pc"));
   CU_TRY(cu.p_cuModuleGetFunction(&gm->params, gm->mod, "inflx_params"));
   CU_TRY(cu.p_cuModuleGetFunction(&gm->rows, gm->mod, "inflx_rows"));
+  if (g->ncf) CU_TRY(cu.p_cuModuleGetFunction(&gm->cols, gm->mod, "inflx_cols"));
   *out = gm.get();
   lib->modules[key] = std::move(gm);
   return INFLX_OK;
@@ -417,7 +419,7 @@ static inflx_status run_shard(inflx_lib* lib, const inflx_grid_request& rq, cons
   GroupModule* gm = nullptr;
   if ((st = load_module(lib, dev, op.group, &gm))) return st;
   const GroupEntry* ge = lib->group(op.group);
-  const uint32_t P = lib->hdr.n_params, NPF = ge->npf, NRF = ge->nrf;
+  const uint32_t P = lib->hdr.n_params, NPF = ge->npf, NRF = ge->nrf, NCF = ge->ncf;
   const uint32_t RPT = lib->hdr.rpt, BLOCK = lib->hdr.block;
   const uint64_t S = sh.se - sh.sb, rows_total = sh.re - sh.rb, n1 = rq.n1;
   if (S == 0 || rows_total == 0 || n1 == 0) return INFLX_OK;
@@ -479,6 +481,7 @@ static inflx_status run_shard(inflx_lib* lib, const inflx_grid_request& rq, cons
     }
   }
   if (NRF && (st = ensure_dev(cu, dev->d_rc, s_chunk * rows_chunk * NRF * 8))) return st;
+  if (NCF && (st = ensure_dev(cu, dev->d_cc, s_chunk * NCF * n1 * 8))) return st;
 
   // host layout of the request: [n_vectors][rows of the REQUEST][n1][k]; hesse: [n_vectors][4][rows][n1]
   const uint64_t req_rows = rq.row_end - rq.row_begin;
@@ -550,6 +553,13 @@ static inflx_status run_shard(inflx_lib* lib, const inflx_grid_request& rq, cons
     const uint64_t sc = std::min(s_chunk, S - s0);
     if (NPF)
       CU_TRY(cu.p_cuMemcpyDtoDAsync(gm->pc_sym, dev->d_pc.ptr + s0 * NPF * 8, sc * NPF * 8, cs));
+    if (NCF) {  // column pre-pass: the column block holds a correctly rounded libm call
+      uint32_t n1c = (uint32_t)n1;
+      void* args[] = {&dev->d_cc.ptr, &of1, &dx1, &n1c};
+      if ((st = launch(cu, gm->cols, (unsigned)((n1 + 127) / 128), (unsigned)sc, 1, 128, cs, args)))
+        return st;
+      res.launches++;
+    }
     for (uint64_t r0 = sh.rb; r0 < sh.re; r0 += rows_chunk, ++k) {
       const uint64_t rc = std::min(rows_chunk, sh.re - r0);
       const int slot = (int)(k & 1);
@@ -592,7 +602,8 @@ static inflx_status run_shard(inflx_lib* lib, const inflx_grid_request& rq, cons
         while (rpt > 2 && ctas(rpt) < 4 * wave) rpt /= 2;
       }
       while (rpt < RPT && (rc + rpt - 1) / rpt > 65535) rpt *= 2;  // gridDim.y limit
-      void* args[] = {&outp, &dev->d_rc.ptr, &of1, &dx1, &n1u, &n_rows, &comp_stride, &aux, &rpt};
+      void* args[] = {&outp, &dev->d_rc.ptr, &of1, &dx1, &n1u, &n_rows, &comp_stride, &aux, &rpt,
+                      &dev->d_cc.ptr};
       if ((st = launch(cu, grid_fn, (unsigned)col_tiles, (unsigned)((rc + rpt - 1) / rpt),
                        (unsigned)sc, BLOCK, cs, args)))
         return st;

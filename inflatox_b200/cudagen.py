@@ -45,6 +45,12 @@ _CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 MIN_BLOCKS = {"cmp": 6, "hes": 6}
 PC_CAPACITY = 7680  # doubles of __constant__ memory for P-frontier values (60 of the 64 KiB)
 MAX_FAST_POW = 64  # |exponent| up to which literal (half-)integer powers use the dd chains
+# libm calls with a correctly rounded double-double implementation (csrc/inflx_crmath.cuh) and the
+# node classes that use it (~1000 FP64 instructions per call: never per grid point; a column
+# block that contains one is evaluated by the `inflx_cols` pre-pass, once per column, instead of
+# once per CTA in the grid kernel's prologue)
+CR_FUNCTIONS = ("pow", "log", "exp", "sin", "cos")
+CR_CLASSES = ("P", "R", "C")
 
 # fixed epilogue cost in flops (a8 as written = 46, a9 = 13; the rest counted the
 # same way: + - * / sqrt and every libm-class call = 1, abs/neg/compare = 0)
@@ -249,8 +255,42 @@ class GroupProgram:
             )
         self.p_slot = {n: k for k, n in enumerate(self.p_frontier)}
         self.r_slot = {n: k for k, n in enumerate(self.r_frontier)}
+        # column pre-pass: only when the column block is expensive (holds a correctly rounded
+        # libm call); a cheap column block stays in the grid kernel's prologue
+        self.cols_prepass = any(
+            self.klass(i) == "C"
+            and self.node(i)[0] == "f"
+            and self.node(i)[1] in CR_FUNCTIONS
+            and self._cr_call(i)
+            for i in self.grid_nodes
+        )
+        self.c_frontier = (
+            [
+                i
+                for i in self.grid_nodes
+                if self.klass(i) == "C"
+                and self.is_op(i)
+                and (
+                    i in grid_root_ids
+                    or any(u in grid_set and self.klass(u) != "C" for u in users.get(i, ()))
+                )
+            ]
+            if self.cols_prepass
+            else []
+        )
+        self.c_slot = {n: k for k, n in enumerate(self.c_frontier)}
         # rows of the row-frontier array are read with 128-bit loads: keep them 16-byte aligned
         self.n_row_slots = (len(self.r_frontier) + 1) & ~1
+
+    def _cr_call(self, i: int) -> bool:
+        """True when the libm call `i` is emitted as an inflx_cr_* function (a pow with a literal
+        (half-)integer exponent uses the double-double chains instead)."""
+        n = self.node(i)
+        if n[1] == "pow" and self.dag.is_const(n[3]):
+            e2 = 2.0 * float(self.dag.cval(n[3]))
+            if e2.is_integer() and 1 <= abs(e2) <= 2 * MAX_FAST_POW:
+                return False
+        return True
 
     def is_op(self, i: int) -> bool:
         return self.node(i)[0] in (
@@ -296,6 +336,7 @@ class GroupProgram:
             "n_p_frontier": len(self.p_frontier),
             "n_r_frontier": len(self.r_frontier),
             "n_row_slots": self.n_row_slots,
+            "n_c_frontier": len(self.c_frontier),
         }
 
     # -- emission ----------------------------------------------------------------------------
@@ -368,6 +409,10 @@ class GroupProgram:
                     return f"inflx_powh_neg<{(-e2 - 1) // 2}>({args[0]}, {pol})"
             if name == "sqrt" and spec:
                 return f"inflx_sqrt_s({args[0]}, bad)"
+            if name in CR_FUNCTIONS and self.klass(i) in CR_CLASSES:
+                # evaluated once per parameter vector / grid row: afford the correctly rounded
+                # double-double version (what glibc returns), see csrc/inflx_crmath.cuh
+                return f"inflx_cr_{name}({', '.join(args)})"
             return f"{name}({', '.join(args)})"
         raise KeyError(f"cannot emit node {i}: {n}")
 
@@ -414,11 +459,14 @@ class GroupProgram:
     def cuda_source(self, model_name: str) -> str:
         with open(os.path.join(_CSRC, "inflx_device.cuh")) as fh:
             device_header = fh.read()
+        with open(os.path.join(_CSRC, "inflx_crmath.cuh")) as fh:
+            device_header += "\n" + fh.read()
         npf, nrf = len(self.p_frontier), self.n_row_slots
         src = [f"#define INFLX_GROUP_MIN_BLOCKS {MIN_BLOCKS.get(self.group, 5)}\n", device_header]
         src.append(f'\n// ===== generated: model "{model_name}", group "{self.group}" =====\n')
         src.append(f"#define INFLX_NP {self.n_params}\n#define INFLX_NPF {npf}\n")
         src.append(f"#define INFLX_NRF {nrf}\n#define INFLX_PC_CAP {PC_CAPACITY}\n")
+        src.append(f"#define INFLX_NCF {len(self.c_frontier)}\n")
         src.append("__constant__ double inflx_pc[INFLX_PC_CAP];\n\n")
 
         # ---- (1) parameter block: one thread per parameter vector ----
@@ -464,6 +512,29 @@ class GroupProgram:
             "  double* __restrict__ rr = rc + ((u64)blockIdx.y * n_rows + i) * INFLX_NRF;\n"
             "  (void)pbase; (void)x0; (void)rr;\n" + body + stores + "}\n\n"
         )
+
+        # ---- (2b) column block as a pre-pass: one thread per (column, parameter vector) ----
+        if self.cols_prepass:
+            scope = {n: f"inflx_pc[pbase + {k}]" for n, k in self.p_slot.items()}
+            scope.update(self._leaf_scope({("x", 1): "x1"}))
+            body = self._block(self.nodes_of("C", self.grid_nodes), scope, "  ", spec=False)
+            for n in self.c_slot:
+                if n not in scope and self.node(n)[0] == "rcp":
+                    body += f"  const double t{n} = {self._expr(n, scope, False)};\n"
+                    scope[n] = f"t{n}"
+            stores = "".join(
+                f"  cc[((u64)blockIdx.y * INFLX_NCF + {k}) * n1 + col] = {self._ref(n, scope)};\n"
+                for n, k in self.c_slot.items()
+            )
+            src.append(
+                "extern \"C\" __global__ void inflx_cols(double* __restrict__ cc, double of1, "
+                "double dx1, u32 n1) {\n"
+                "  const u32 col = blockIdx.x * blockDim.x + threadIdx.x;\n"
+                "  if (col >= n1) return;\n"
+                "  const u32 pbase = blockIdx.y * INFLX_NPF;\n"
+                "  const double x1 = inflx_coord(col, dx1, of1);\n"
+                "  (void)pbase; (void)x1;\n" + body + stores + "}\n\n"
+            )
 
         # ---- (3) slow path + grid kernels: thread = column, walks INFLX_RPT rows ----
         src.append(self._slow_function())
@@ -545,8 +616,17 @@ class GroupProgram:
         pbase = "pbase + " if sweep else ""
         scope = {n: f"inflx_pc[{pbase}{k}]" for n, k in self.p_slot.items()}
         scope.update(self._leaf_scope({("x", 1): "x1"}))
-        col_block = self._block(self.nodes_of("C", self.grid_nodes), scope, "  ", spec=True)
-        col_block = col_block.replace(", bad)", ", bad_c)").replace("(bad)", "(bad_c)")
+        if self.cols_prepass:
+            # column-frontier values come from the inflx_cols pre-pass: coalesced loads
+            col_block = "  const u32 ccol = active ? col : 0u;\n"
+            for n, k in self.c_slot.items():
+                col_block += (
+                    f"  const double t{n} = __ldg(cc + ((u64)s * INFLX_NCF + {k}) * n1 + ccol);\n"
+                )
+                scope[n] = f"t{n}"
+        else:
+            col_block = self._block(self.nodes_of("C", self.grid_nodes), scope, "  ", spec=True)
+            col_block = col_block.replace(", bad)", ", bad_c)").replace("(bad)", "(bad_c)")
         lazy = {n: f"__ldg(rr + {k})" for n, k in self.r_slot.items()}
         mixed = self._block(self.nodes_of("M", self.grid_nodes), scope, "    ", True, lazy)
         root_loads = ""
@@ -569,7 +649,8 @@ class GroupProgram:
         return (
             f"extern \"C\" __global__ void __launch_bounds__(INFLX_BLOCK, INFLX_MIN_BLOCKS) {name}("
             "double* __restrict__ out, const double* __restrict__ rc, double of1, double dx1, "
-            "u32 n1, u32 n_rows, u64 comp_stride, double aux, u32 rpt) {\n"
+            "u32 n1, u32 n_rows, u64 comp_stride, double aux, u32 rpt, "
+            "const double* __restrict__ cc) {\n"
             "  const u32 col = blockIdx.x * INFLX_BLOCK + threadIdx.x;\n"
             + (
                 "  const u32 s = blockIdx.z;\n  const u32 pbase = s * INFLX_NPF;\n"
@@ -594,7 +675,7 @@ class GroupProgram:
             "  const bool active = col < n1;\n"
             "  const double x1 = inflx_coord(active ? col : 0u, dx1, of1);\n"
             "  bool bad_c = false;\n"
-            "  (void)x1; (void)aux; (void)comp_stride; (void)rc; (void)pbase;\n"
+            "  (void)x1; (void)aux; (void)comp_stride; (void)rc; (void)pbase; (void)cc;\n"
             + col_block
             + "#if INFLX_NRF > 0\n  __syncthreads();\n#endif\n"
             "  if (!active) return;\n"

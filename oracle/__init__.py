@@ -112,14 +112,26 @@ class _Build:
             os.replace(tmp, out)
         return out
 
-    def model(self, name: str, quad: bool = False, contract: str = "off") -> str:
-        """Compile the reference-generated C of `name` with the reference's flags."""
+    def model(self, name: str, quad: bool = False, contract: str = "off", libm: str = "glibc") -> str:
+        """Compile the reference-generated C of `name` with the reference's flags.
+
+        `libm="cr"` is an ATTRIBUTION variant, not the parity oracle: the same text with libm's
+        log / exp / pow / sin / cos replaced by the correctly rounded versions of
+        inflatox_b200/csrc/inflx_crmath.cuh (host build).  Comparing the CUDA path with both
+        shows which part of a residue is glibc's own misrounding (~1e-3 of the pow calls)."""
         tag = "quad" if quad else f"fpc_{contract}"
+        if libm == "cr":
+            with open(os.path.join(ROOT, "inflatox_b200", "csrc", "inflx_crmath.cuh"), "rb") as fh:
+                tag += "_cr" + hashlib.sha1(fh.read()).hexdigest()[:8]
         out = os.path.join(self.dir, f"{name}.{tag}.so")
         if not os.path.exists(out):
             text = golden_c_text(name)
             if quad:
                 text = quad_transliteration(text)
+            elif libm == "cr":
+                hdr = os.path.join(ROOT, "inflatox_b200", "csrc", "inflx_crmath.cuh")
+                defs = "".join(f"#define {f} inflx_cr_{f}\n" for f in ("log", "exp", "pow", "sin", "cos"))
+                text = text.replace("#include <math.h>", f'#include <math.h>\n#include "{hdr}"\n{defs}', 1)
             src = os.path.join(self.dir, f"{name}.{tag}.c")
             with open(src, "w") as fh:
                 fh.write(text)
@@ -128,7 +140,10 @@ class _Build:
                 cmd = ["gcc", "-O1", "-fpic", "-shared", "-std=gnu17", "-o", tmp, src,
                        "-lquadmath", "-lm"]  # fmt: skip
             else:
-                cmd = ["gcc", "-o", tmp, src, *REFERENCE_FLAGS, f"-ffp-contract={contract}"]
+                flags = REFERENCE_FLAGS
+                if libm == "cr":  # the header's unused static functions would trip -Werror
+                    flags = [f for f in flags if f not in ("-Wall", "-Werror")]
+                cmd = ["gcc", "-o", tmp, src, *flags, f"-ffp-contract={contract}"]
             _run(cmd)
             os.replace(tmp, out)
         return out
@@ -154,13 +169,13 @@ def build_all(models=MODELS, quad: bool = False) -> str:
 class Oracle:
     """ctypes front-end of one model artefact opened by the restated loader."""
 
-    def __init__(self, model: str, quad: bool = False, contract: str = "off"):
+    def __init__(self, model: str, quad: bool = False, contract: str = "off", libm: str = "glibc"):
         global _build
         _build = _build or _Build()
         self.quad = quad
         self.sfx = "_quad" if quad else ""
         self.lib = ctypes.CDLL(_build.driver(quad))
-        self.path = _build.model(model, quad=quad, contract=contract)
+        self.path = _build.model(model, quad=quad, contract=contract, libm=libm)
         self.h = ctypes.c_void_p()
         fn = self._fn("oracle_open")
         fn.restype = ctypes.c_int

@@ -185,3 +185,74 @@ def test_atan_tan_helper_accuracy(mod):
     assert worst_t <= 3.0, worst_t
     assert d[-6] == 0.0 and t[-6] == 0.0  # y = 0
     assert d[-4] == 1.5707963267948966 and abs(t[-4] / 1.633123935319537e16 - 1) < 1e-15  # y = inf
+
+
+# ---------------------------------------------------------------------------------------------
+# correctly rounded libm subset (csrc/inflx_crmath.cuh): the device build must return the bits of
+# the host build of the same file, which tests/test_crmath.py proves correctly rounded
+# ---------------------------------------------------------------------------------------------
+CR_SRC = r"""
+extern "C" __global__ void t_cr(const double* x, const double* y, double* p, double* l, double* e,
+                                double* s, double* c, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  p[i] = inflx_cr_pow(x[i], y[i]);
+  l[i] = inflx_cr_log(x[i]);
+  e[i] = inflx_cr_exp(y[i]);
+  s[i] = inflx_cr_sin(y[i]);
+  c[i] = inflx_cr_cos(y[i]);
+}
+"""
+CR_HOST = r"""
+#include INFLX_CRMATH_HEADER
+void host_cr(const double* x, const double* y, double* p, double* l, double* e, double* s,
+             double* c, long n) {
+  for (long i = 0; i < n; i++) {
+    p[i] = inflx_cr_pow(x[i], y[i]);
+    l[i] = inflx_cr_log(x[i]);
+    e[i] = inflx_cr_exp(y[i]);
+    s[i] = inflx_cr_sin(y[i]);
+    c[i] = inflx_cr_cos(y[i]);
+  }
+}
+"""
+
+
+@pytest.mark.parametrize("fmad", [False, True])
+def test_correctly_rounded_libm_matches_the_host_build(tmp_path, fmad):
+    import ctypes
+    import os
+    import subprocess
+
+    from gpu_kernels import ROOT, Module
+
+    header = os.path.join(ROOT, "inflatox_b200", "csrc", "inflx_crmath.cuh")
+    src, so = tmp_path / "host_cr.c", tmp_path / "host_cr.so"
+    src.write_text(CR_HOST)
+    subprocess.run(
+        ["gcc", "-O2", "-march=native", "-ffp-contract=off", "-shared", "-fPIC",
+         f'-DINFLX_CRMATH_HEADER="{header}"', str(src), "-o", str(so), "-lm"], check=True,
+    )  # fmt: skip
+    host = ctypes.CDLL(str(so))
+    rng = np.random.default_rng(5)
+    n = 1 << 18
+    x = np.ascontiguousarray(np.exp(rng.uniform(-30, 30, n)))
+    y = np.ascontiguousarray(rng.uniform(-20, 20, n))
+    x[:4], y[:4] = [0.47, 0.5, 1.0, 25098.05], [-1.5, -3.0, 7.0, 0.3]  # EGNO / d5 magnitudes
+    x[4:10] = [0.0, -1.0, np.inf, np.nan, 5e-324, 1e308]   # irregular: libm / libdevice path
+    outs_d = [np.zeros(n) for _ in range(5)]
+    outs_h = [np.zeros(n) for _ in range(5)]
+    with open(header) as fh:
+        mod = Module(fh.read() + CR_SRC, fmad=fmad)
+    mod.launch("t_cr", n, [x, y], outs_d)
+    dp = ctypes.POINTER(ctypes.c_double)
+    host.host_cr(*[a.ctypes.data_as(dp) for a in [x, y] + outs_h], ctypes.c_long(n))
+    regular = np.ones(n, dtype=bool)
+    regular[4:10] = False
+    for name, d, h in zip(("pow", "log", "exp", "sin", "cos"), outs_d, outs_h):
+        same = _same(d, h)
+        assert same[regular].all(), (name, int((~same[regular]).sum()))
+    # irregular arguments: same class of result (NaN / inf / zero) as libm
+    for d, h in zip(outs_d[:2], outs_h[:2]):
+        assert (np.isnan(d[4:10]) == np.isnan(h[4:10])).all()
+        assert (np.isinf(d[4:10]) == np.isinf(h[4:10])).all()

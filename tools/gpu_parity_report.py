@@ -64,6 +64,8 @@ def main():
     ap.add_argument("--quad", action="store_true")
     ap.add_argument("--quad-n", type=int, default=96)
     ap.add_argument("--fmad", action="store_true")
+    ap.add_argument("--cr", action="store_true",
+                    help="also compare with the oracle variant whose libm is correctly rounded")
     ap.add_argument("--models", nargs="*", default=list(cases.MODELS))
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
@@ -87,6 +89,11 @@ def main():
         out1 = np.zeros((n, n))
         rs.consistency_only(lib, p, out1, ss, False, 0)
         entry["consistency_only"] = stats(out1, orc.consistency_only(p, n, n, ext))
+        if a.cr:
+            ref_cr = oracle.Oracle(m, libm="cr").complete_analysis(p, n, n, ext)
+            entry["complete_analysis_vs_cr_libm_oracle"] = {
+                NAMES6[k]: stats(out[..., k], ref_cr[..., k]) for k in range(6)
+            }
         if a.quad:
             qn = a.quad_n
             oq = oracle.Oracle(m, quad=True)
