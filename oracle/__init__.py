@@ -122,7 +122,7 @@ class _Build:
         tag = "quad" if quad else f"fpc_{contract}"
         if libm == "cr":
             with open(os.path.join(ROOT, "inflatox_b200", "csrc", "inflx_crmath.cuh"), "rb") as fh:
-                tag += "_cr" + hashlib.sha1(fh.read()).hexdigest()[:8]
+                tag += "_cr2" + hashlib.sha1(fh.read()).hexdigest()[:8]
         out = os.path.join(self.dir, f"{name}.{tag}.so")
         if not os.path.exists(out):
             text = golden_c_text(name)
@@ -130,8 +130,21 @@ class _Build:
                 text = quad_transliteration(text)
             elif libm == "cr":
                 hdr = os.path.join(ROOT, "inflatox_b200", "csrc", "inflx_crmath.cuh")
-                defs = "".join(f"#define {f} inflx_cr_{f}\n" for f in ("log", "exp", "pow", "sin", "cos"))
-                text = text.replace("#include <math.h>", f'#include <math.h>\n#include "{hdr}"\n{defs}', 1)
+                # a negative base with an integer exponent (fields range over negative values and the
+                # text is full of pow(x, 3)): correctly rounded through |x|, sign restored
+                wrap = (
+                    "static double inflx_oracle_cr_pow(double x, double y) {\n"
+                    "  if (x < 0 && y == rint(y) && fabs(y) < 9e15) {\n"
+                    "    const double r = inflx_cr_pow(-x, y);\n"
+                    "    return fmod(fabs(y), 2.0) == 1.0 ? -r : r;\n"
+                    "  }\n"
+                    "  return inflx_cr_pow(x, y);\n"
+                    "}\n#define pow inflx_oracle_cr_pow\n"
+                )
+                defs = "".join(f"#define {f} inflx_cr_{f}\n" for f in ("log", "exp", "sin", "cos"))
+                text = text.replace(
+                    "#include <math.h>", f'#include <math.h>\n#include "{hdr}"\n{wrap}{defs}', 1
+                )
             src = os.path.join(self.dir, f"{name}.{tag}.c")
             with open(src, "w") as fh:
                 fh.write(text)

@@ -35,17 +35,18 @@ def test_gpu_error_within_cpu_error_envelope(model, n):
         assert np.median(eg[both]) <= 2 * np.median(ec[both]) + 1e-15, (model, k)
 
 
-@pytest.mark.parametrize("model", ["egno", "d5"])
+@pytest.mark.parametrize("model", ["angular", "egno", "d5"])
 def test_residue_against_the_oracle_is_glibc_misrounding(model):
-    """Attribution of what is left of the parity residue on the two ill-conditioned models.
+    """Attribution of what is left of the parity residue on the three ill-conditioned models.
 
     The CUDA path evaluates the hoisted libm calls (EGNO: pow(x, -3 alpha) once per row; d5: log per
     row, sin / cos per column) correctly rounded (csrc/inflx_crmath.cuh).  glibc's pow is not
     correctly rounded in ~1e-3 of its calls (tests/test_crmath.py), which on EGNO hits a handful
-    of whole rows and is amplified past 1e-10 by the model's cancellation.  Against the oracle
-    variant whose libm IS correctly rounded - same generated C, same flags, same restated loop -
-    every finite point agrees within 1e-10, NaN masks included (measured: 100 % on all planes,
-    max 1.1e-12; profiles/parity_cr_r1.json)."""
+    of whole rows (angular: rows and columns, through the hoisted pow(x, n)) and is amplified past
+    1e-10 by the model's cancellation.  Against the oracle variant whose libm IS correctly rounded
+    - same generated C, same flags, same restated loop - every finite point agrees within 1e-10,
+    NaN masks included (measured: 100 % on all planes of all three models, max 1.1e-11;
+    profiles/parity_cr_r1.json)."""
     n = 512
     lib = rs.open_inflx_dylib(cases.artifact(model).shared_object_path, False)
     lib.set_devices([0])

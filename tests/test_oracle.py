@@ -87,3 +87,18 @@ def test_quad_truth_brackets_the_double_oracle():
     q = oracle.Oracle("doc", quad=True).complete_analysis(p, 24, 24, ext)
     err, fin, nan_mm, _ = cases.rel_err(a[..., 1], q[..., 1])
     assert nan_mm == 0 and err[fin].max() < 1e-13
+
+
+def test_correctly_rounded_libm_variant_attributes_glibc_misrounding():
+    """`Oracle(model, libm="cr")` (attribution variant, not the parity oracle): the same generated C
+    with log / exp / pow / sin / cos correctly rounded.  It must agree with the plain oracle wherever
+    glibc is correctly rounded - i.e. on all but a few rows / columns of an ill-conditioned model -
+    and everywhere on a model without such calls on its hoisted path."""
+    n = 128
+    for model, floor in (("doc", 1.0), ("egno", 0.95), ("angular", 0.99)):
+        p, ext = cases.params(model), cases.EXTENT[model]
+        a = oracle.Oracle(model).complete_analysis(p, n, n, ext)
+        b = oracle.Oracle(model, libm="cr").complete_analysis(p, n, n, ext)
+        err, fin, nan_mm, inf_mm = cases.rel_err(b, a)
+        assert nan_mm == 0 and inf_mm == 0
+        assert (err[fin] <= 1e-10).mean() >= floor, model
