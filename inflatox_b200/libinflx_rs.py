@@ -385,7 +385,9 @@ class _PageableBlock:
         return (self.buf.ctypes.data + 63) & ~63
 
 
-_pool_lock = threading.Lock()
+# re-entrant: a lease's __del__ (below) takes it too, and the cyclic GC may run that finaliser on
+# the very thread that is inside one of the locked regions
+_pool_lock = threading.RLock()
 _pin_pool: dict[int, list[_PinnedBlock]] = {}
 _page_pool: dict[int, list[_PageableBlock]] = {}
 _pin_jobs: dict[int, threading.Thread] = {}
