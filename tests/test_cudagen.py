@@ -59,4 +59,43 @@ def test_literal_powers_use_the_double_double_chains():
     unit = cexpr.parse_c_unit(oracle.golden_c_text("egno"))
     src = cudagen.ModelProgram(unit).groups["cmp"].cuda_source("egno")
     assert "inflx_powi<3>(" in src and "inflx_powh<1>(" in src and "inflx_powh_neg<0>(" in src
-    assert "pow(" in src  # the symbolic exponent -3*alpha stays a libdevice pow
+    # the symbolic exponent -3*alpha: evaluated once per row, correctly rounded
+    assert "inflx_cr_pow(" in src
+
+
+def test_hoisted_libm_calls_are_correctly_rounded_and_expensive_columns_get_a_prepass():
+    """log / exp / pow / sin / cos of classes P, R, C go through csrc/inflx_crmath.cuh; a column
+    block that holds one is evaluated by the `inflx_cols` pre-pass (d5: sin, cos), every other
+    model keeps its (cheap) column block in the grid kernel's prologue."""
+    import re
+
+    progs = {
+        m: cudagen.ModelProgram(cexpr.parse_c_unit(oracle.golden_c_text(m)))
+        for m in ("angular", "egno", "d5")
+    }
+    for m, prog in progs.items():
+        for g, gp in prog.groups.items():
+            assert gp.cols_prepass == (m == "d5"), (m, g)
+            src = gp.cuda_source(m)
+            assert ("void inflx_cols(" in src) == gp.cols_prepass
+            assert f"#define INFLX_NCF {len(gp.c_frontier)}\n" in src
+            for i in gp.all_nodes:
+                n = gp.node(i)
+                if n[0] == "f" and n[1] in cudagen.CR_FUNCTIONS and gp._cr_call(i):
+                    # no such call is ever evaluated per grid point in the test models
+                    assert gp.klass(i) in cudagen.CR_CLASSES, (m, g, n)
+            # the generated part (after the headers) spells no plain libm call of that set
+            gen = src[src.index("// ===== generated"):]
+            assert not re.search(r"(?<![A-Za-z_])(log|exp|sin|cos)\(", gen), (m, g)
+    gp = progs["d5"].groups["cmp"]
+    src = gp.cuda_source("d5")
+    cols = src[src.index("void inflx_cols("):src.index("inflx_slow_roots")]
+    assert "inflx_cr_cos(x1)" in cols and "inflx_cr_sin(x1)" in cols
+    grid = src[src.index("void __launch_bounds__(INFLX_BLOCK, INFLX_MIN_BLOCKS) inflx_grid_complete_analysis("):]
+    grid = grid[: grid.index("#pragma unroll 1")]
+    assert grid.count("__ldg(cc + ") == len(gp.c_frontier) and "inflx_cr_" not in grid
+    # frontier completeness for the column pre-pass: M nodes read C values through a slot
+    for i in gp.nodes_of("M", gp.grid_nodes):
+        for o in gp.operands(i):
+            if gp.klass(o) == "C" and gp.is_op(o):
+                assert o in gp.c_slot
