@@ -3,7 +3,7 @@
 Compares cudaHostAlloc with mmap(+MADV_HUGEPAGE) -> parallel pre-fault -> cudaHostRegister, and
 checks that the D2H DMA rate into either kind of block is the same.  Feeds the design of
 inflx_host_alloc (end-to-end section)."""
-import ctypes, mmap, sys, time, threading
+import ctypes, sys, time, threading
 import torch
 
 GB = 1 << 30
