@@ -241,14 +241,15 @@ def test_basis_validation():
         rs.open_inflx_dylib(art.shared_object_path, True)
 
 
-def test_multi_device_row_sharding_in_one_process():
+@pytest.mark.parametrize("model", ["angular", "d5"])  # d5: column pre-pass on every device
+def test_multi_device_row_sharding_in_one_process(model):
     from inflatox_b200 import _native
 
     n_dev = _native.lib().inflx_device_count()
     if n_dev < 2:
         pytest.skip("needs >= 2 GPUs")
-    lib = rs.open_inflx_dylib(cases.artifact("angular").shared_object_path, False)
-    p, ext = cases.params("angular"), cases.EXTENT["angular"]
+    lib = rs.open_inflx_dylib(cases.artifact(model).shared_object_path, False)
+    p, ext = cases.params(model), cases.EXTENT[model]
     lib.set_devices([0])
     one = np.zeros((N0, N1, 6))
     rs.grid_eval(lib, "complete_analysis", p, one, N0, N1, ext)
