@@ -109,3 +109,32 @@ def test_product_code_never_touches_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", text, re.M), f
                 assert "liboracle" not in text and "oracle/" not in text.replace("# oracle/", ""), f
+
+
+def test_cpp_host_example_builds_against_the_header_and_fails_loudly_without_a_gpu(tmp_path):
+    """examples/complete_analysis.cpp: a C++ embedder over include/inflx_b200.h only.  It must
+    compile warning-free, read the artefact's metadata without a GPU, and - on a box without a
+    CUDA driver - stop with the engine's own message instead of producing numbers."""
+    import subprocess
+
+    from inflatox_b200 import _native
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    _native.lib()  # builds the engine in tree if it is missing
+    libdir = os.path.dirname(_native.LIB_PATH)
+    exe = tmp_path / "complete_analysis"
+    subprocess.run(
+        ["g++", "-std=c++17", "-Wall", "-Werror", f"-I{root}/include",
+         f"{root}/examples/complete_analysis.cpp", "-o", str(exe), f"-L{libdir}", "-linflx_b200",
+         f"-Wl,-rpath,{libdir}"], check=True,
+    )  # fmt: skip
+    art = cases.artifact("doc")
+    r = subprocess.run(
+        [str(exe), art.shared_object_path, "32", "32", "0", "2.5", "0", "3.14", "1.0"],
+        capture_output=True, text=True,
+    )  # fmt: skip
+    assert "2 fields, 1 parameters, artefact ABI 5.0.0" in r.stdout
+    if _native.lib().inflx_device_count() < 1:
+        assert r.returncode == 1 and "failed (status 9)" in r.stderr
+    else:
+        assert r.returncode == 0 and "consistency" in r.stdout
