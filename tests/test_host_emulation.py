@@ -1,0 +1,167 @@
+"""The GENERATED CUDA translation units, executed on the host (tests/native/cuda_host_shim.h +
+emulate.cpp): parameter block, row / column pre-passes, grid kernels (plain and sweep), smem
+staging, frontier slots, slow path - the same source text NVRTC compiles, one emulated thread per
+CTA, launched in the engine's order.  This checks the generator (rate partition, frontiers,
+hoisted reciprocals, correctly rounded hoisted libm calls, epilogues, stores) against the oracle
+without a GPU; the GPU tests then only have to establish that the device executes that text the
+way the host does (tests/test_gpu_*.py).
+
+Not emulated exactly: the two hardware seeds (MUFU.RCP64H / RSQ64H) are IEEE values here.  The
+refined quotient / root is the correctly rounded one either way for operands the fast path
+accepts; correction terms that use a bare seed (half-integer powers, atan for y > 1) may differ
+in the last bit in ~1e-7 of the calls."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import cases
+import oracle
+from inflatox_b200 import cexpr, cudagen
+from raw_units import N_PAR, RawOracle, make_unit
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+NATIVE = os.path.join(ROOT, "tests", "native")
+_DP = ctypes.POINTER(ctypes.c_double)
+_PER_POINT = {"complete_analysis": 6, "hesse": 4}
+
+
+class Emulated:
+    """One generated translation unit + one grid op, compiled for the host."""
+
+    def __init__(self, program, name: str, group: str, op: str, workdir, rpt_max: int = 16):
+        cu = os.path.join(str(workdir), f"{name}_{group}.cu")
+        if not os.path.exists(cu):
+            with open(cu, "w") as fh:
+                fh.write(program.groups[group].cuda_source(name))
+        so = os.path.join(str(workdir), f"emu_{name}_{group}_{op}.so")
+        subprocess.run(
+            ["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fopenmp", "-shared", "-fPIC",
+             "-DINFLX_BLOCK=1", f"-DINFLX_RPT={rpt_max}", f'-DINFLX_GENERATED_CU="{cu}"',
+             f"-DINFLX_EMU_KERNEL=inflx_grid_{op}", f"-DINFLX_EMU_KERNEL_SWEEP=inflx_grid_{op}_sweep",
+             f"-I{NATIVE}", os.path.join(NATIVE, "emulate.cpp"), "-o", so],
+            check=True,
+        )  # fmt: skip
+        self.lib = ctypes.CDLL(so)
+        self.lib.emu_grid.argtypes = [
+            _DP, ctypes.c_uint, _DP, ctypes.c_ulonglong, ctypes.c_uint, _DP, ctypes.c_ulonglong,
+            ctypes.c_ulonglong, ctypes.c_uint, ctypes.c_double,
+        ]  # fmt: skip
+        self.op, self.per = op, _PER_POINT.get(op, 1)
+
+    def grid(self, p, n0, n1, ext, rows=None, rpt=16, aux=0.0):
+        p2 = np.ascontiguousarray(np.atleast_2d(np.asarray(p, dtype=np.float64)))
+        s = p2.shape[0]
+        r0, r1 = rows if rows is not None else (0, n0)
+        if self.op == "hesse":
+            out = np.full((4, s, r1 - r0, n1), -7.0)
+        else:
+            out = np.full((s, r1 - r0, n1, self.per), -7.0)  # every element must be overwritten
+        ss = np.ascontiguousarray(ext, dtype=np.float64)
+        rc = self.lib.emu_grid(p2.ctypes.data_as(_DP), s, out.ctypes.data_as(_DP), n0, n1,
+                               ss.ctypes.data_as(_DP), r0, r1, rpt, aux)  # fmt: skip
+        assert rc == 0
+        if self.op == "hesse":
+            return out[:, 0] if np.ndim(p) == 1 else out
+        out = out[..., 0] if self.per == 1 else out
+        return out[0] if np.ndim(p) == 1 else out
+
+
+def _program(model):
+    return cudagen.ModelProgram(cexpr.parse_c_unit(oracle.golden_c_text(model)))
+
+
+def _same_bits(a, b):
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    return (a.view(np.uint64) == b.view(np.uint64)) | (np.isnan(a) & np.isnan(b)) | ((a == 0) & (b == 0))
+
+
+@pytest.fixture(scope="module")
+def workdir(tmp_path_factory):
+    return tmp_path_factory.mktemp("emu")
+
+
+@pytest.mark.parametrize("model", cases.MODELS)
+def test_generated_kernels_reproduce_the_oracle(model, workdir):
+    """complete_analysis on a ragged 61 x 83 grid: NaN / inf masks of the oracle, every finite point
+    within 1e-10 of the correctly-rounded-libm oracle variant, >= 98 % within 1e-10 of the plain
+    one (the difference is glibc's own misrounding on a few rows / columns)."""
+    emu = Emulated(_program(model), model, "cmp", "complete_analysis", workdir)
+    p, ext, n0, n1 = cases.params(model), cases.EXTENT[model], 61, 83
+    got = emu.grid(p, n0, n1, ext)
+    assert not (got == -7.0).any()
+    ref = oracle.Oracle(model).complete_analysis(p, n0, n1, ext)
+    ref_cr = oracle.Oracle(model, libm="cr").complete_analysis(p, n0, n1, ext)
+    err, fin, nan_mm, inf_mm = cases.rel_err(got, ref)
+    assert nan_mm == 0 and inf_mm == 0
+    assert (err[fin] <= 1e-10).mean() >= 0.98
+    err, fin, nan_mm, inf_mm = cases.rel_err(got, ref_cr)
+    assert nan_mm == 0 and inf_mm == 0
+    assert (err[fin] <= 1e-10).all(), float(err[fin].max())
+
+
+@pytest.mark.parametrize("model", ["angular", "d5"])  # d5: column pre-pass
+def test_launch_geometry_does_not_change_a_bit(model, workdir):
+    emu = Emulated(_program(model), model, "cmp", "complete_analysis", workdir)
+    p, ext, n0, n1 = cases.params(model), cases.EXTENT[model], 45, 37
+    base = emu.grid(p, n0, n1, ext, rpt=16)
+    for rpt in (1, 2, 5, 8):  # rows per CTA: the engine's launch argument
+        assert _same_bits(emu.grid(p, n0, n1, ext, rpt=rpt), base).all(), rpt
+    # a row shard uses global coordinates
+    part = emu.grid(p, n0, n1, ext, rows=(13, 40), rpt=4)
+    assert _same_bits(part, base[13:40]).all()
+
+
+@pytest.mark.parametrize("model", ["hyper", "d5"])
+def test_sweep_kernel_equals_one_launch_per_vector(model, workdir):
+    emu = Emulated(_program(model), model, "cmp", "complete_analysis", workdir)
+    rng = np.random.default_rng(3)
+    p0 = cases.params(model)
+    ps = np.stack([p0, p0 * (1 + 0.1 * rng.random(p0.size)), p0 * (1 - 0.1 * rng.random(p0.size))])
+    ext, n0, n1 = cases.EXTENT[model], 33, 29
+    fused = emu.grid(ps, n0, n1, ext, rpt=8)
+    assert fused.shape == (3, n0, n1, 6)
+    for k in range(3):
+        assert _same_bits(fused[k], emu.grid(ps[k], n0, n1, ext, rpt=8)).all(), k
+
+
+def test_single_plane_and_array_ops(workdir):
+    prog, model = _program("angular"), "angular"
+    p, ext, n0, n1 = cases.params(model), cases.EXTENT[model], 40, 52
+    orc = oracle.Oracle(model, libm="cr")
+    for group, op, ref in (
+        ("con", "consistency_only", orc.consistency_only(p, n0, n1, ext)),
+        ("con", "consistency_rapidturn_only", orc.consistency_rapidturn_only(p, n0, n1, ext)),
+        ("eps", "epsilon_v_only", orc.epsilon_v_only(p, n0, n1, ext)),
+        ("pot", "potential", orc.potential_array(p, n0, n1, ext)),
+        ("hes", "hesse", orc.hesse_array(p, n0, n1, ext).reshape(4, n0, n1)),
+    ):
+        got = Emulated(prog, model, group, op, workdir).grid(p, n0, n1, ext)
+        err, fin, nan_mm, inf_mm = cases.rel_err(got, ref)
+        assert nan_mm == 0 and inf_mm == 0, op
+        assert (err[fin] <= 1e-10).all(), (op, float(err[fin].max()))
+
+
+@pytest.mark.parametrize("seed,conditionals", [(0, False), (1, False), (2, False), (100, True), (101, True)])
+def test_random_arithmetic_models_are_bit_identical_on_the_host(seed, conditionals, tmp_path):
+    """The CPU twin of tests/test_gpu_random_models.py: random units made of + - * / sqrt fabs
+    pow(., 2) (and comparisons / ?: when `conditionals`), gcc against the generated kernels."""
+    c_text = make_unit(seed, conditionals)
+    orc = RawOracle(c_text, str(tmp_path))
+    prog = cudagen.ModelProgram(cexpr.parse_c_unit(c_text))
+    rng = np.random.default_rng(seed)
+    p = rng.uniform(0.5, 3.0, N_PAR)
+    ext, n0, n1 = (-2.0, 3.0, -1.5, 2.5), 37, 59
+    v = Emulated(prog, "rnd", "pot", "potential", tmp_path).grid(p, n0, n1, ext)
+    assert _same_bits(v, orc.potential_array(p, n0, n1, ext)).all()
+    h = Emulated(prog, "rnd", "hes", "hesse", tmp_path).grid(p, n0, n1, ext)
+    assert _same_bits(h, orc.hesse_array(p, n0, n1, ext).reshape(4, n0, n1)).all()
+    out = Emulated(prog, "rnd", "cmp", "complete_analysis", tmp_path).grid(p, n0, n1, ext)
+    ref = orc.complete_analysis(p, n0, n1, ext)
+    for k in (0, 1, 2, 5):  # every plane that is pure IEEE arithmetic
+        same = _same_bits(out[..., k], ref[..., k])
+        assert same.all(), (seed, k, int((~same).sum()))
+    for k in (3, 4):
+        assert (np.isnan(out[..., k]) == np.isnan(ref[..., k])).all()
