@@ -88,6 +88,44 @@ def make_unit(seed: int, conditionals: bool = False) -> str:
     return text
 
 
+# zero / inf / subnormal / huge / NaN operands in every class (parameter, row, column, point)
+SPECIAL_UNIT = PREAMBLE % (N_PAR, 999) + """
+double V(const double x[], const double args[]){
+    return (x[1] + 2)/(x[0]) + (x[1])/(args[0]*x[0]) + (x[0])/(x[1]);
+}
+double v00(const double x[], const double args[]){
+    return (x[1])/(args[1]) + sqrt(x[0] - 1)*x[1];
+}
+double v01(const double x[], const double args[]){
+    return (x[1]*x[0])/(args[2]);
+}
+double v10(const double x[], const double args[]){
+    return (x[0] - x[1])/((x[0])*(x[0]) - 1);
+}
+double v11(const double x[], const double args[]){
+    return (1.0/3.0)/(x[1]) + (x[0])/(args[0]);
+}
+double grad_norm_squared(const double x[], const double args[]){
+    return ((x[1])/(x[0]))/(x[1] - x[0]);
+}
+double inner_prod(const double x[], const double args[], const double v1[], const double v2[]){
+    const double g00 = 1;
+    const double g11 = 1;
+    return 0.0 + (g00 * v1[0] * v2[0]) + (g11 * v1[1] * v2[1]);
+}
+void v(const double x[], const double args[], double v_out[]){
+    v_out[0] = x[0];
+    v_out[1] = x[1];
+    return;
+}
+void w1(const double x[], const double args[], double v_out[]){
+    v_out[0] = x[1];
+    v_out[1] = x[0];
+    return;
+}
+"""
+
+
 class RawOracle(oracle.Oracle):
     """oracle driver over an arbitrary generated C unit (same reference flag set)."""
 

@@ -165,3 +165,30 @@ def test_random_arithmetic_models_are_bit_identical_on_the_host(seed, conditiona
         assert same.all(), (seed, k, int((~same).sum()))
     for k in (3, 4):
         assert (np.isnan(out[..., k]) == np.isnan(ref[..., k])).all()
+
+
+@pytest.mark.parametrize(
+    "params",
+    [[1.0, 2.0, 3.0], [1e308, 0.0, 1e-320], [np.inf, -0.0, np.nan], [3e-310, 1e300, 5e-324]],
+)
+def test_irregular_operands_take_the_exact_path_on_the_host(params, tmp_path):
+    """CPU twin of the GPU test of the same name: zero, infinite, subnormal, huge and NaN operands
+    in every class; the generated validity tests must send those points to the IEEE slow path
+    (`inflx_slow_roots`) - results equal gcc's bit for bit, signs of infinities included."""
+    from raw_units import SPECIAL_UNIT
+
+    orc = RawOracle(SPECIAL_UNIT, str(tmp_path))
+    prog = cudagen.ModelProgram(cexpr.parse_c_unit(SPECIAL_UNIT))
+    p = np.array(params, dtype=np.float64)
+    ext, n0, n1 = (-1.0, 3.0, -2.0, 2.0), 16, 32  # contains x0 = 0, +-1, x1 = 0, x0 = x1 exactly
+    v = Emulated(prog, "special", "pot", "potential", tmp_path).grid(p, n0, n1, ext)
+    assert _same_bits(v, orc.potential_array(p, n0, n1, ext)).all()
+    h = Emulated(prog, "special", "hes", "hesse", tmp_path).grid(p, n0, n1, ext)
+    assert _same_bits(h, orc.hesse_array(p, n0, n1, ext).reshape(4, n0, n1)).all()
+    out = Emulated(prog, "special", "cmp", "complete_analysis", tmp_path).grid(p, n0, n1, ext)
+    ref = orc.complete_analysis(p, n0, n1, ext)
+    for k in (0, 1, 2, 5):
+        ok = _same_bits(out[..., k], ref[..., k])
+        assert ok.all(), (k, out[..., k][~ok][:4], ref[..., k][~ok][:4])
+    assert (np.isnan(out[..., 3:5]) == np.isnan(ref[..., 3:5])).all()
+    assert (np.isinf(out[..., 3:5]) == np.isinf(ref[..., 3:5])).all()
