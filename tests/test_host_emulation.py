@@ -9,7 +9,11 @@ way the host does (tests/test_gpu_*.py).
 Not emulated exactly: the two hardware seeds (MUFU.RCP64H / RSQ64H) are IEEE values here.  The
 refined quotient / root is the correctly rounded one either way for operands the fast path
 accepts; correction terms that use a bare seed (half-integer powers, atan for y > 1) may differ
-in the last bit in ~1e-7 of the calls."""
+in the last bit in ~1e-7 of the calls.  libm calls outside the correctly rounded set (tanh, sinh,
+...) resolve to the HOST's libm here and to libdevice on the GPU (hyperinflation model: the GPU's
+eps_H / omega differ from the oracle in the last bit on 20-30 % of the points, the emulation does
+not).  On 512^2 grids the emulation reproduces the GPU's parity statistics against the oracle
+digit for digit for doc, angular, EGNO and d5 (profiles/parity_r1.json; DESIGN.md)."""
 import ctypes
 import os
 import subprocess
