@@ -196,3 +196,76 @@ def test_irregular_operands_take_the_exact_path_on_the_host(params, tmp_path):
         assert ok.all(), (k, out[..., k][~ok][:4], ref[..., k][~ok][:4])
     assert (np.isnan(out[..., 3:5]) == np.isnan(ref[..., 3:5])).all()
     assert (np.isinf(out[..., 3:5]) == np.isinf(ref[..., 3:5])).all()
+
+
+TRANSCENDENTAL_UNIT = """
+double V(const double x[], const double args[]){
+    return exp(-x[0]*x[1])*cos(x[0] + x[1]) + args[0]*log(2 + x[0]*x[0]*x[1]*x[1]) + pow(1 + x[0]*x[0], args[1]);
+}
+double v00(const double x[], const double args[]){
+    return pow(2 + x[0]*x[1]*x[1], args[2]) + sin(x[1])*tanh(x[0]);
+}
+double v01(const double x[], const double args[]){
+    return atan(x[0]*x[1]) + sinh(0.25*x[0]);
+}
+double v10(const double x[], const double args[]){
+    return exp(0.5*x[1]) - log(3 + x[0]) + 0.125;
+}
+double v11(const double x[], const double args[]){
+    return cos(x[0]*x[1]) + pow(args[0], x[1]) + 2;
+}
+double grad_norm_squared(const double x[], const double args[]){
+    return pow(x[0]*x[0] + x[1]*x[1] + 1, 1.5) + exp(args[1]);
+}
+double inner_prod(const double x[], const double args[], const double v1[], const double v2[]){
+    const double g00 = 1;
+    const double g11 = 1;
+    return 0.0 + (g00 * v1[0] * v2[0]) + (g11 * v1[1] * v2[1]);
+}
+void v(const double x[], const double args[], double v_out[]){
+    v_out[0] = x[0];
+    v_out[1] = x[1];
+    return;
+}
+void w1(const double x[], const double args[], double v_out[]){
+    v_out[0] = x[1];
+    v_out[1] = x[0];
+    return;
+}
+"""
+
+
+def test_libm_calls_in_every_class(tmp_path):
+    """exp / log / pow / sin / cos / tanh / sinh / atan of parameters, rows, columns and of both
+    coordinates: hoisted calls of the correctly rounded set go through inflx_cr_*, per-point
+    (class M) ones stay plain libm calls (libdevice on the GPU), and the unit evaluates to the
+    oracle's values (the emulation's libm is the oracle's, so only glibc-vs-correctly-rounded
+    last bits of the hoisted calls can differ)."""
+    from raw_units import PREAMBLE
+
+    c_text = PREAMBLE % (N_PAR, 7) + TRANSCENDENTAL_UNIT
+    orc = RawOracle(c_text, str(tmp_path))
+    prog = cudagen.ModelProgram(cexpr.parse_c_unit(c_text))
+    gp = prog.groups["cmp"]
+    classes = {}
+    for i in gp.grid_nodes:
+        n = gp.node(i)
+        if n[0] == "f" and n[1] not in ("sqrt", "fabs"):
+            classes.setdefault(gp.klass(i), set()).add(n[1])
+    assert {"exp", "cos", "log", "pow"} <= classes["M"]
+    assert "pow" in classes["R"] and "exp" in classes["P"] and {"sin", "exp"} <= classes["C"]
+    assert gp.cols_prepass  # sin(x1), exp(x1/2) are correctly rounded calls of the column block
+    src = gp.cuda_source("transc")
+    grid = src[src.index("inflx_grid_complete_analysis("):]
+    loop = grid[grid.index("#pragma unroll 1"): grid.index("inflx_grid_complete_analysis_sweep")]
+    assert " exp(" in loop and " cos(" in loop and "inflx_cr_" not in loop
+    p = np.array([1.5, 0.75, -1.25])
+    ext, n0, n1 = (0.1, 2.0, -1.0, 1.5), 41, 53
+    out = Emulated(prog, "transc", "cmp", "complete_analysis", tmp_path).grid(p, n0, n1, ext)
+    ref = orc.complete_analysis(p, n0, n1, ext)
+    err, fin, nan_mm, inf_mm = cases.rel_err(out, ref)
+    assert nan_mm == 0 and inf_mm == 0 and fin.any()
+    assert (err[fin] <= 1e-12).all(), float(err[fin].max())
+    h = Emulated(prog, "transc", "hes", "hesse", tmp_path).grid(p, n0, n1, ext)
+    err, fin, nan_mm, inf_mm = cases.rel_err(h, orc.hesse_array(p, n0, n1, ext).reshape(4, n0, n1))
+    assert nan_mm == 0 and (err[fin] <= 1e-14).all(), float(err[fin].max())
