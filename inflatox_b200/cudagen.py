@@ -45,10 +45,23 @@ _CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 MIN_BLOCKS = {"cmp": 6, "hes": 6}
 PC_CAPACITY = 7680  # doubles of __constant__ memory for P-frontier values (60 of the 64 KiB)
 MAX_FAST_POW = 64  # |exponent| up to which literal (half-)integer powers use the dd chains
-# libm calls with a correctly rounded double-double implementation (csrc/inflx_crmath.cuh) and the
-# node classes that use it (~1000 FP64 instructions per call: never per grid point; a column
-# block that contains one is evaluated by the `inflx_cols` pre-pass, once per column, instead of
-# once per CTA in the grid kernel's prologue)
+# libm flavours for the model's libm calls in the hoisted node classes P / R / C (a column block
+# that contains such a call is evaluated by the `inflx_cols` pre-pass, once per column, instead of
+# once per CTA in the grid kernel's prologue):
+#   "glibc"  (default) csrc/inflx_glibcmath.cuh: the algorithm glibc 2.39 runs on the reference's
+#            host, bit for bit - the reference's own result (compiler.py:299-310 links -lm).  Also
+#            used for pow(x, n) with a literal n in those classes, because glibc's pow is not always
+#            correctly rounded and the dd chains are.  60-100 FP64 instructions per call.
+#   "cr"     csrc/inflx_crmath.cuh: correctly rounded in double-double arithmetic (~1000 FP64
+#            instructions per call); literal powers through the correctly rounded dd chains.
+#   "device" libdevice everywhere (1-2 ulp).
+# Per grid point (class M) a libm call uses libdevice and a literal (half-)integer power the
+# correctly rounded dd chain (EGNO: pow(., -0.5), pow(., 1.5); d5: pow(., 1.5)) - except in flavour
+#   "glibc-all" = "glibc" + the class-M calls of GL_FUNCTIONS through inflx_gl_* as well (bit
+#            identity with the reference wherever glibc's pow misrounds, at 60-100 FP64
+#            instructions and an out-of-line call per point; measured in DESIGN.md).
+LIBM_FLAVOURS = ("glibc", "glibc-all", "cr", "device")
+GL_FUNCTIONS = ("pow", "log", "exp", "expm1", "sin", "cos", "tanh")
 CR_FUNCTIONS = ("pow", "log", "exp", "sin", "cos")
 CR_CLASSES = ("P", "R", "C")
 
@@ -133,10 +146,13 @@ class GroupProgram:
     parameter-class denominator costs 3 FP64 instructions instead of 9.
     """
 
-    def __init__(self, dag: Dag, roots: ModelRoots, group: str, n_params: int):
+    def __init__(self, dag: Dag, roots: ModelRoots, group: str, n_params: int, libm: str = "glibc"):
+        if libm not in LIBM_FLAVOURS:
+            raise Exception(f"unknown libm flavour {libm!r}: one of {LIBM_FLAVOURS}")
         self.dag = dag
         self.group = group
         self.n_params = n_params
+        self.libm = libm
         grid_names, point_names, self.grid_ops, self.point_ops = GROUPS[group]
         self.grid_roots = {n: roots.node[n] for n in grid_names}
         self.point_roots = {n: roots.node[n] for n in grid_names + point_names}
@@ -258,10 +274,7 @@ class GroupProgram:
         # column pre-pass: only when the column block is expensive (holds a correctly rounded
         # libm call); a cheap column block stays in the grid kernel's prologue
         self.cols_prepass = any(
-            self.klass(i) == "C"
-            and self.node(i)[0] == "f"
-            and self.node(i)[1] in CR_FUNCTIONS
-            and self._cr_call(i)
+            self.klass(i) == "C" and self.node(i)[0] == "f" and self._hoisted_libm(i) is not None
             for i in self.grid_nodes
         )
         self.c_frontier = (
@@ -282,15 +295,24 @@ class GroupProgram:
         # rows of the row-frontier array are read with 128-bit loads: keep them 16-byte aligned
         self.n_row_slots = (len(self.r_frontier) + 1) & ~1
 
-    def _cr_call(self, i: int) -> bool:
-        """True when the libm call `i` is emitted as an inflx_cr_* function (a pow with a literal
-        (half-)integer exponent uses the double-double chains instead)."""
+    def _hoisted_libm(self, i: int) -> str | None:
+        """Prefix of the out-of-line libm function ("inflx_gl_" / "inflx_cr_") the call node `i` is
+        emitted with, None when it is emitted inline (libdevice, dd power chains, sqrt, fabs)."""
         n = self.node(i)
-        if n[1] == "pow" and self.dag.is_const(n[3]):
-            e2 = 2.0 * float(self.dag.cval(n[3]))
-            if e2.is_integer() and 1 <= abs(e2) <= 2 * MAX_FAST_POW:
-                return False
-        return True
+        if self.libm == "glibc-all" and n[1] in GL_FUNCTIONS and self.klass(i) in "PRCM":
+            return "inflx_gl_"
+        if self.klass(i) not in CR_CLASSES:
+            return None
+        if self.libm == "glibc" and n[1] in GL_FUNCTIONS:
+            return "inflx_gl_"
+        if self.libm == "cr" and n[1] in CR_FUNCTIONS:
+            if n[1] == "pow" and self.dag.is_const(n[3]):
+                # correctly rounded either way: the dd chains are ~100x cheaper
+                e2 = 2.0 * float(self.dag.cval(n[3]))
+                if e2.is_integer() and 1 <= abs(e2) <= 2 * MAX_FAST_POW:
+                    return None
+            return "inflx_cr_"
+        return None
 
     def is_op(self, i: int) -> bool:
         return self.node(i)[0] in (
@@ -394,6 +416,11 @@ class GroupProgram:
         if k == "f":
             name = n[1]
             args = [self._ref(a, scope) for a in n[2:]]
+            hoisted = self._hoisted_libm(i)
+            if hoisted is not None:
+                # evaluated once per parameter vector / grid row / grid column: afford the
+                # reference's own libm (or the correctly rounded one), see LIBM_FLAVOURS
+                return f"{hoisted}{name}({', '.join(args)})"
             if name == "pow" and d.is_const(n[3]):
                 e = float(d.cval(n[3]))
                 if e.is_integer() and 1 <= abs(e) <= MAX_FAST_POW:
@@ -409,10 +436,6 @@ class GroupProgram:
                     return f"inflx_powh_neg<{(-e2 - 1) // 2}>({args[0]}, {pol})"
             if name == "sqrt" and spec:
                 return f"inflx_sqrt_s({args[0]}, bad)"
-            if name in CR_FUNCTIONS and self.klass(i) in CR_CLASSES:
-                # evaluated once per parameter vector / grid row: afford the correctly rounded
-                # double-double version (what glibc returns), see csrc/inflx_crmath.cuh
-                return f"inflx_cr_{name}({', '.join(args)})"
             return f"{name}({', '.join(args)})"
         raise KeyError(f"cannot emit node {i}: {n}")
 
@@ -459,8 +482,14 @@ class GroupProgram:
     def cuda_source(self, model_name: str) -> str:
         with open(os.path.join(_CSRC, "inflx_device.cuh")) as fh:
             device_header = fh.read()
-        with open(os.path.join(_CSRC, "inflx_crmath.cuh")) as fh:
-            device_header += "\n" + fh.read()
+        if self.libm == "cr":
+            with open(os.path.join(_CSRC, "inflx_crmath.cuh")) as fh:
+                device_header += "\n" + fh.read()
+        elif self.libm in ("glibc", "glibc-all"):
+            with open(os.path.join(_CSRC, "inflx_glibc_tables.cuh")) as fh:
+                tables = fh.read()
+            with open(os.path.join(_CSRC, "inflx_glibcmath.cuh")) as fh:
+                device_header += "\n" + fh.read().replace('#include "inflx_glibc_tables.cuh"', tables)
         npf, nrf = len(self.p_frontier), self.n_row_slots
         src = [f"#define INFLX_GROUP_MIN_BLOCKS {MIN_BLOCKS.get(self.group, 5)}\n", device_header]
         src.append(f'\n// ===== generated: model "{model_name}", group "{self.group}" =====\n')
@@ -771,7 +800,8 @@ class GroupProgram:
 class ModelProgram:
     """All groups of one model + the metadata the artefact header carries."""
 
-    def __init__(self, unit: ParsedUnit):
+    def __init__(self, unit: ParsedUnit, libm: str = "glibc"):
+        self.libm = libm
         if unit.dim != 2:
             raise Exception(
                 f"the CUDA back-end evaluates 2-field models (the model has {unit.dim} fields)"
@@ -779,7 +809,7 @@ class ModelProgram:
         self.unit = unit
         self.roots = ModelRoots(unit)
         self.groups = {
-            g: GroupProgram(unit.dag, self.roots, g, unit.n_parameters or 0) for g in GROUPS
+            g: GroupProgram(unit.dag, self.roots, g, unit.n_parameters or 0, libm) for g in GROUPS
         }
 
     def flops_per_point(self, op: str) -> int:
@@ -803,4 +833,4 @@ class ModelProgram:
             for op in set(grid_ops) | set(point_ops):
                 if op != "basis":
                     flops[op] = self.flops_per_point(op)
-        return {"groups": meta, "flops_per_point": flops}
+        return {"groups": meta, "flops_per_point": flops, "libm": self.libm}

@@ -33,19 +33,29 @@ def params(model):
 
 
 @functools.lru_cache(maxsize=None)
-def artifact(model: str, fmad: bool = False):
+def golden_cse(model: str) -> bool:
+    """Whether the reference's test compiles this model with cse=True (tests/golden/c/*.json)."""
+    import json
+
+    with open(os.path.join(GOLDEN, "c", f"{model}.json")) as fh:
+        return bool(json.load(fh)["cse"])
+
+
+@functools.lru_cache(maxsize=None)
+def artifact(model: str, fmad: bool = False, libm: str | None = None):
     """Compile the pickled reference-built model with inflatox_b200.Compiler (cached per process;
-    cubins additionally cached on disk by content hash)."""
+    cubins additionally cached on disk by content hash).  `libm`: flavour of the hoisted libm
+    calls (cudagen.LIBM_FLAVOURS), default = the Compiler's."""
     import inflatox_b200 as ix
-    import oracle
 
     m = ix.InflationModel.load(os.path.join(GOLDEN, "models", f"{model}.pkl.gz"))
     flags = None
     if fmad:
         flags = [f.replace("--fmad=false", "--fmad=true") for f in ix.Compiler.default_nvrtc_flags]
-    return ix.Compiler(
-        m, silent=True, cse=oracle.golden_meta(model)["cse"], cleanup=True, compiler_flags=flags
-    ).compile()
+    c = ix.Compiler(m, silent=True, cse=golden_cse(model), cleanup=True, compiler_flags=flags)
+    if libm is not None:
+        c.libm = libm
+    return c.compile()
 
 
 def trajectory(model: str) -> np.ndarray:

@@ -19,7 +19,8 @@ class Module:
         from inflatox_b200.compiler import nvrtc_compile
 
         self.cu = cu
-        opts = ["--gpu-architecture=sm_100a", "--std=c++17", f"--fmad={'true' if fmad else 'false'}"]
+        opts = ["--gpu-architecture=sm_100a", "--std=c++17", f"--fmad={'true' if fmad else 'false'}",
+                "--prec-div=true", "--prec-sqrt=true"]
         cubin = nvrtc_compile(device_header() + source, "test_kernels.cu", opts)
         (err,) = cu.cuInit(0)
         assert err == cu.CUresult.CUDA_SUCCESS, err

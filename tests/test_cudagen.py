@@ -55,47 +55,74 @@ def test_emitted_cuda_compiles_for_sm_100a(program):
     assert cubin[:4] == b"\x7fELF"
 
 
-def test_literal_powers_use_the_double_double_chains():
+def test_libm_flavours_of_the_hoisted_calls():
+    """EGNO: pow(x, 3), pow(x, 3/2), pow(x, -1/2) and the symbolic exponent -3*alpha, all per row.
+    Default flavour: the reference host's libm bit for bit (inflx_gl_pow, literal exponents
+    included: glibc's pow is not always the correctly rounded value the dd chains return);
+    "cr": correctly rounded (dd chains for the literal powers); "device": libdevice."""
     unit = cexpr.parse_c_unit(oracle.golden_c_text("egno"))
     src = cudagen.ModelProgram(unit).groups["cmp"].cuda_source("egno")
+    gen = src[src.index("// ===== generated"):]
+    assert "inflx_gl_pow(" in gen and "inflx_cr_" not in src
+    rows = gen[gen.index("void inflx_rows("):gen.index("inflx_slow_roots")]
+    assert "inflx_powi<" not in rows and "inflx_powh" not in rows  # no dd chain in a hoisted class
+    src = cudagen.ModelProgram(unit, libm="cr").groups["cmp"].cuda_source("egno")
     assert "inflx_powi<3>(" in src and "inflx_powh<1>(" in src and "inflx_powh_neg<0>(" in src
-    # the symbolic exponent -3*alpha: evaluated once per row, correctly rounded
-    assert "inflx_cr_pow(" in src
+    assert "inflx_cr_pow(" in src and "inflx_gl_" not in src
+    src = cudagen.ModelProgram(unit, libm="device").groups["cmp"].cuda_source("egno")
+    assert "inflx_cr_" not in src and "inflx_gl_" not in src and " pow(" in src
+    with pytest.raises(Exception, match="unknown libm flavour"):
+        cudagen.ModelProgram(unit, libm="musl")
 
 
-def test_hoisted_libm_calls_are_correctly_rounded_and_expensive_columns_get_a_prepass():
-    """log / exp / pow / sin / cos of classes P, R, C go through csrc/inflx_crmath.cuh; a column
-    block that holds one is evaluated by the `inflx_cols` pre-pass (d5: sin, cos), every other
-    model keeps its (cheap) column block in the grid kernel's prologue."""
+def test_hoisted_libm_calls_use_the_reference_libm_and_expensive_columns_get_a_prepass():
+    """log / exp / pow / sin / cos / tanh of classes P, R, C go through csrc/inflx_glibcmath.cuh; a
+    column block that holds one is evaluated by the `inflx_cols` pre-pass (d5: sin, cos; angular:
+    pow(x1, n)), a pure-arithmetic column block stays in the grid kernel's prologue (EGNO)."""
     import re
 
     progs = {
         m: cudagen.ModelProgram(cexpr.parse_c_unit(oracle.golden_c_text(m)))
-        for m in ("angular", "egno", "d5")
+        for m in ("hyper", "angular", "egno", "d5")
     }
     for m, prog in progs.items():
         for g, gp in prog.groups.items():
-            assert gp.cols_prepass == (m == "d5"), (m, g)
+            col_calls = [
+                i for i in gp.grid_nodes
+                if gp.node(i)[0] == "f" and gp.klass(i) == "C" and gp._hoisted_libm(i)
+            ]
+            assert gp.cols_prepass == bool(col_calls), (m, g)
             src = gp.cuda_source(m)
             assert ("void inflx_cols(" in src) == gp.cols_prepass
             assert f"#define INFLX_NCF {len(gp.c_frontier)}\n" in src
             for i in gp.all_nodes:
                 n = gp.node(i)
-                if n[0] == "f" and n[1] in cudagen.CR_FUNCTIONS and gp._cr_call(i):
-                    # no such call is ever evaluated per grid point in the test models
-                    assert gp.klass(i) in cudagen.CR_CLASSES, (m, g, n)
+                if n[0] == "f" and n[1] in cudagen.GL_FUNCTIONS:
+                    if gp.klass(i) == "M":
+                        # the only per-point calls of the test models: pow(., 3/2), pow(., -1/2)
+                        # (EGNO, d5) - dd chains by default, inflx_gl_pow in flavour "glibc-all"
+                        assert n[1] == "pow" and gp.dag.cval(n[3]) in (1.5, -0.5), (m, g, n)
+                        assert gp._hoisted_libm(i) is None
+                    else:
+                        assert gp._hoisted_libm(i) == "inflx_gl_"
             # the generated part (after the headers) spells no plain libm call of that set
             gen = src[src.index("// ===== generated"):]
-            assert not re.search(r"(?<![A-Za-z_])(log|exp|sin|cos)\(", gen), (m, g)
+            assert not re.search(r"(?<![A-Za-z_])(log|exp|sin|cos|tanh|pow)\(", gen), (m, g)
+            if m == "egno" and g == "cmp":
+                all_src = cudagen.ModelProgram(prog.unit, libm="glibc-all").groups[g].cuda_source(m)
+                loop = all_src[all_src.index("#pragma unroll 1"):]
+                assert "inflx_gl_pow(" in loop[: loop.index("inflx_grid_complete_analysis_sweep")]
+    assert progs["d5"].groups["cmp"].cols_prepass and not progs["egno"].groups["cmp"].cols_prepass
     gp = progs["d5"].groups["cmp"]
     src = gp.cuda_source("d5")
     cols = src[src.index("void inflx_cols("):src.index("inflx_slow_roots")]
-    assert "inflx_cr_cos(x1)" in cols and "inflx_cr_sin(x1)" in cols
+    assert "inflx_gl_cos(x1)" in cols and "inflx_gl_sin(x1)" in cols
     grid = src[src.index("void __launch_bounds__(INFLX_BLOCK, INFLX_MIN_BLOCKS) inflx_grid_complete_analysis("):]
     grid = grid[: grid.index("#pragma unroll 1")]
-    assert grid.count("__ldg(cc + ") == len(gp.c_frontier) and "inflx_cr_" not in grid
+    assert grid.count("__ldg(cc + ") == len(gp.c_frontier) and "inflx_gl_" not in grid
     # frontier completeness for the column pre-pass: M nodes read C values through a slot
     for i in gp.nodes_of("M", gp.grid_nodes):
         for o in gp.operands(i):
             if gp.klass(o) == "C" and gp.is_op(o):
                 assert o in gp.c_slot
+    assert "inflx_gl_tanh(" in progs["hyper"].groups["cmp"].cuda_source("hyper")

@@ -256,3 +256,82 @@ def test_correctly_rounded_libm_matches_the_host_build(tmp_path, fmad):
     for d, h in zip(outs_d[:2], outs_h[:2]):
         assert (np.isnan(d[4:10]) == np.isnan(h[4:10])).all()
         assert (np.isinf(d[4:10]) == np.isinf(h[4:10])).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference host's libm restated (csrc/inflx_glibcmath.cuh): the device build must return the
+# bits of the HOST'S libm itself (tests/test_glibcmath.py proves the host build does)
+# ---------------------------------------------------------------------------------------------
+GL_SRC = r"""
+extern "C" __global__ void t_gl(const double* x, const double* y, double* p, double* l, double* e,
+                                double* s, double* c, double* t, double* m, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  p[i] = inflx_gl_pow(x[i], y[i]);
+  l[i] = inflx_gl_log(x[i]);
+  e[i] = inflx_gl_exp(y[i]);
+  s[i] = inflx_gl_sin(y[i]);
+  c[i] = inflx_gl_cos(y[i]);
+  t[i] = inflx_gl_tanh(y[i]);
+  m[i] = inflx_gl_expm1(y[i]);
+}
+"""
+GL_HOST = r"""
+#include <math.h>
+void host_libm(const double* x, const double* y, double* p, double* l, double* e, double* s,
+               double* c, double* t, double* m, long n) {
+  for (long i = 0; i < n; i++) {
+    p[i] = pow(x[i], y[i]);
+    l[i] = log(x[i]);
+    e[i] = exp(y[i]);
+    s[i] = sin(y[i]);
+    c[i] = cos(y[i]);
+    t[i] = tanh(y[i]);
+    m[i] = expm1(y[i]);
+  }
+}
+"""
+
+
+@pytest.mark.parametrize("fmad", [False, True])
+def test_glibc_libm_on_the_device_has_the_bits_of_the_host_libm(tmp_path, fmad):
+    import ctypes
+    import os
+    import subprocess
+
+    from gpu_kernels import ROOT, Module
+    from test_glibcmath import _has_fma, _host_glibc
+
+    if not (_host_glibc() == "2.39" and _has_fma()):
+        pytest.skip("bit identity is pinned to glibc 2.39's FMA ifunc variants")
+    csrc = os.path.join(ROOT, "inflatox_b200", "csrc")
+    src, so = tmp_path / "host_libm.c", tmp_path / "host_libm.so"
+    src.write_text(GL_HOST)
+    subprocess.run(["gcc", "-O2", "-fno-builtin", "-shared", "-fPIC", str(src), "-o", str(so), "-lm"],
+                   check=True)  # fmt: skip
+    host = ctypes.CDLL(str(so))
+    rng = np.random.default_rng(6)
+    n = 1 << 21
+    q = n // 4
+    x = np.empty(n)
+    y = np.empty(n)
+    x[:q], y[:q] = np.exp(rng.uniform(-30, 30, q)), rng.uniform(-20, 20, q)
+    x[q:2 * q], y[q:2 * q] = rng.uniform(0.4, 0.6, q), -3.0 * rng.uniform(0.05, 2.0, q)  # EGNO rows
+    x[2 * q:3 * q] = rng.uniform(0, 36, q)                                               # d5 rows
+    y[2 * q:3 * q] = np.where(rng.random(q) < 0.5, rng.integers(1, 9, q) * 0.5, 4 * np.pi * rng.random(q))
+    x[3 * q:], y[3 * q:] = _random_doubles(rng, n - 3 * q), _random_doubles(rng, n - 3 * q)[::-1]
+    x, y = np.ascontiguousarray(x), np.ascontiguousarray(y)
+    outs_d = [np.zeros(n) for _ in range(7)]
+    outs_h = [np.zeros(n) for _ in range(7)]
+    with open(os.path.join(csrc, "inflx_glibc_tables.cuh")) as fh:
+        tables = fh.read()
+    with open(os.path.join(csrc, "inflx_glibcmath.cuh")) as fh:
+        header = fh.read().replace('#include "inflx_glibc_tables.cuh"', tables)
+    mod = Module(header + GL_SRC, fmad=fmad)
+    mod.launch("t_gl", n, [x, y], outs_d)
+    dp = ctypes.POINTER(ctypes.c_double)
+    host.host_libm(*[a.ctypes.data_as(dp) for a in [x, y] + outs_h], ctypes.c_long(n))
+    for name, d, h in zip(("pow", "log", "exp", "sin", "cos", "tanh", "expm1"), outs_d, outs_h):
+        same = _same(d, h)
+        bad = np.flatnonzero(~same)
+        assert same.all(), (name, bad.size, x[bad[:3]], y[bad[:3]], d[bad[:3]], h[bad[:3]])

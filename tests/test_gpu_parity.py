@@ -1,13 +1,13 @@
 """Parity of the CUDA path (through the C ABI / the drop-in module) with the CPU oracle.
 
 Bar (BASELINE.json north_star): NaN / +-inf masks bit-identical; <= 1e-10 relative error per
-finite point.  +,-,*,/,sqrt and literal (half-)integer powers are evaluated bit-identically by
-construction; libm-class calls (general pow, log, sin, cos, tanh, atan, tan) differ by <= 1-2 ulp
-between libdevice and glibc, and the models' projected-Hesse expressions amplify that wherever
-they cancel catastrophically (the reference's own CPU path moves by more than 1e-10
-on the same points when only its FMA contraction mode changes).  So: well-conditioned models /
-planes must meet 1e-10 on EVERY finite point; for the ill-conditioned ones >= 98.5 % of the finite
-points must, and tests/test_gpu_truth.py bounds the remainder against a __float128 evaluation.
+finite point - asserted here for EVERY finite point of every model, plane and entry point.
++,-,*,/,sqrt are evaluated bit-identically by construction, and the model's hoisted libm calls
+(pow, log, exp, sin, cos, tanh per parameter vector / row / column) return the bits of the
+reference host's glibc (csrc/inflx_glibcmath.cuh): round 1's residue (EGNO 99.0-99.7 %, angular
+99.87-100 % within 1e-10) was glibc's own misrounding of a row-level pow, amplified by the
+models' conditioning.  What may still differ in the last bits: the epilogue's atan / tan
+(delta, eta) and per-point literal half-integer powers (correctly rounded dd chains).
 """
 import ctypes
 import math
@@ -22,7 +22,6 @@ from inflatox_b200 import libinflx_rs as rs
 pytestmark = pytest.mark.gpu
 
 N0, N1 = 203, 157  # ragged on purpose: neither a multiple of the CTA width nor of rows/thread
-WELL_CONDITIONED = {"doc", "hyper"}
 
 
 @pytest.fixture(scope="module", params=cases.MODELS)
@@ -37,13 +36,14 @@ def ss_of(ext):
     return np.array([[ext[0], ext[1]], [ext[2], ext[3]]])
 
 
-def check(model, got, ref, min_frac=0.985, what=""):
+def check(model, got, ref, what=""):
+    """north_star's bar, no allowance: masks identical, every finite point within 1e-10."""
     err, fin, nan_mm, inf_mm = cases.rel_err(got, ref)
     assert nan_mm == 0, f"{model} {what}: {nan_mm} NaN-mask mismatches"
     assert inf_mm == 0, f"{model} {what}: {inf_mm} inf-mask mismatches"
-    frac = float((err[fin] <= 1e-10).mean()) if fin.any() else 1.0
-    need = 1.0 if model in WELL_CONDITIONED else min_frac
-    assert frac >= need, f"{model} {what}: only {frac:.5f} of finite points within 1e-10"
+    n_bad = int((err[fin] > 1e-10).sum())
+    worst = float(err[fin].max()) if fin.any() else 0.0
+    assert n_bad == 0, f"{model} {what}: {n_bad} of {int(fin.sum())} finite points beyond 1e-10 (max {worst:.3g})"
 
 
 def test_complete_analysis(setup):
@@ -72,14 +72,15 @@ def test_flag_quantum_dif(setup):
     x = np.zeros((N0, N1), dtype=bool)
     rs.flag_quantum_dif_py(lib, p, x, ss_of(ext), False, acc)
     ref = orc.flag_quantum_dif(p, N0, N1, ext, acc)
-    assert (x != ref).mean() <= 1e-4, f"{m}: {(x != ref).sum()} flags differ"
+    assert x.any() and not x.all()
+    assert (x != ref).sum() == 0, f"{m}: {(x != ref).sum()} flags differ"
 
 
 def test_potential_and_hesse_arrays(setup):
     m, lib, orc, p, ext = setup
     v = np.zeros((N0, N1))
     lib.potential_array(v, p, ss_of(ext))
-    check(m, v, orc.potential_array(p, N0, N1, ext), min_frac=0.999, what="potential_array")
+    check(m, v, orc.potential_array(p, N0, N1, ext), what="potential_array")
     h = lib.hesse_array(np.array([N0, N1]), p, ss_of(ext))
     assert h.shape == (2, 2, N0, N1)
     ref = orc.hesse_array(p, N0, N1, ext)
@@ -135,6 +136,26 @@ def test_fused_sweep_equals_separate_calls(setup):
         assert np.array_equal(fused[s], one, equal_nan=True), (m, s)
 
 
+def test_c5_parameter_vectors_against_the_oracle():
+    """BASELINE C5's own inputs: the 1024 default_rng(0) vectors (L ~ U(0.05, 2), m ~ 10^U(-3, 1),
+    phi0 ~ U(-1, 1); tanh(x / L) reaches |x / L| = 20), every one against the oracle on a 64 x 64
+    grid through the fused sweep."""
+    import bench
+
+    model, op, _, _, S, ext, ps = bench.workload("C5")
+    assert model == "hyper" and S == 1024 and ps.shape == (1024, 3)
+    lib = rs.open_inflx_dylib(cases.artifact(model).shared_object_path, False)
+    lib.set_devices([0])
+    orc = oracle.Oracle(model)
+    n = 64
+    fused = np.zeros((S, n, n, 6))
+    rs.sweep(lib, "complete_analysis", ps, fused, ext)
+    for k in range(S):
+        ref = orc.complete_analysis(np.ascontiguousarray(ps[k]), n, n, ext)
+        for c in range(6):
+            check(model, fused[k, ..., c], ref[..., c], what=f"C5 vector {k} plane {c}")
+
+
 def test_device_resident_output_equals_host_output(setup):
     import torch
 
@@ -160,11 +181,11 @@ def test_on_trajectory(model):
     rs.complete_analysis_on_trajectory(lib, p, xs, out, False, 1)
     ref = orc.complete_analysis_on_trajectory(p, xs)
     for k in range(6):
-        check(model, out[:, k], ref[:, k], min_frac=0.97, what=f"ot[{k}]")
+        check(model, out[:, k], ref[:, k], what=f"ot[{k}]")
     for fn in ("consistency_only", "consistency_rapidturn_only", "epsilon_v_only"):
         o1 = np.zeros(xs.shape[0])
         getattr(rs, fn + "_on_trajectory")(lib, p, xs, o1, False, 1)
-        check(model, o1, getattr(orc, fn + "_on_trajectory")(p, xs), min_frac=0.97, what=fn)
+        check(model, o1, getattr(orc, fn + "_on_trajectory")(p, xs), what=fn)
 
 
 def test_edge_shapes():
@@ -195,7 +216,7 @@ def test_full_size_rows_of_baseline_grids():
             got = np.zeros((2, n, per) if per > 1 else (2, n))
             rs.grid_eval(lib, op, p, got, n, n, ext, rows=(r, r + 2))
             ref = getattr(orc, op)(p, n, n, ext, rows=(r, r + 2))
-            check(model, got, ref, min_frac=0.97, what=f"{op} rows {r}..{r + 2} of {n}^2")
+            check(model, got, ref, what=f"{op} rows {r}..{r + 2} of {n}^2")
 
 
 def test_full_size_c1_grid():
@@ -273,17 +294,17 @@ def test_reference_test_flows_through_the_facade(model):
     orc = oracle.Oracle(model)
     v = anguelova.calc_V_array(args, [extent[0], extent[2]], [extent[1], extent[3]], [N, N])
     assert v.shape == (N, N)
-    check(model, v, orc.potential_array(args, N, N, extent), min_frac=0.999, what="calc_V_array")
+    check(model, v, orc.potential_array(args, N, N, extent), what="calc_V_array")
     out = anguelova.complete_analysis(args, *extent, *[N, N])
     assert len(out) == 6 and all(o.shape == (N, N) for o in out)
     ref = orc.complete_analysis(args, N, N, extent)
     for k in range(6):
-        check(model, out[k], ref[..., k], min_frac=0.97, what=f"facade plane {k}")
+        check(model, out[k], ref[..., k], what=f"facade plane {k}")
     traj = cases.trajectory(model)
     ot = anguelova.complete_analysis_ot(args, traj)
     assert len(ot) == 6 and ot[0].shape == (traj.shape[0], 1)
     rt = anguelova.consistency_rapidturn(args, *extent, *[N, N])
-    check(model, rt, orc.consistency_rapidturn_only(args, N, N, extent), min_frac=0.97, what="rapidturn")
+    check(model, rt, orc.consistency_rapidturn_only(args, N, N, extent), what="rapidturn")
     assert anguelova.consistency(args, *extent, N, N).shape == (N, N)
     assert anguelova.epsilon_v(args, *extent, N, N).shape == (N, N)
     assert anguelova.consistency_ot(args, traj).shape == (traj.shape[0],)

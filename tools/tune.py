@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Kernel-only timing of compile-time variants (rows per thread, CTA width, register cap, fmad)
-of the grid kernel on a GPU box.  Usage: python tools/tune.py egno complete_analysis 8192"""
+of the grid kernel on a GPU box.  Usage: python tools/tune.py egno complete_analysis 8192 ['[{"rpt": 16, "block": 128, "minb": 5, "extra": ["-DINFLX_EXPERIMENT_RCP4"], "libm": "glibc-all"}]']"""
 import itertools
 import json
 import os
@@ -15,7 +15,6 @@ import numpy as np
 import torch
 
 import cases
-import oracle
 import inflatox_b200 as ix
 from inflatox_b200 import libinflx_rs as rs
 
@@ -24,7 +23,7 @@ def main():
     model, op, n = sys.argv[1], sys.argv[2], int(sys.argv[3])
     variants = json.loads(sys.argv[4]) if len(sys.argv) > 4 else None
     m = ix.InflationModel.load(os.path.join(cases.GOLDEN, "models", f"{model}.pkl.gz"))
-    cse = oracle.golden_meta(model)["cse"]
+    cse = cases.golden_cse(model)
     per = 6 if op == "complete_analysis" else 1
     d = torch.empty(n * n * per, dtype=torch.float64, device="cuda:0")
     p, ext = cases.params(model), cases.EXTENT[model]
@@ -38,7 +37,10 @@ def main():
                  "--prec-sqrt=true", "-lineinfo", f"-DINFLX_RPT={v['rpt']}",
                  f"-DINFLX_BLOCK={v["block"]}"] + ([f"-DINFLX_MIN_BLOCKS={v["minb"]}"] if "minb" in v else []) + v.get("extra", [])
         try:
-            art = ix.Compiler(m, silent=True, cse=cse, compiler_flags=flags).compile()
+            comp = ix.Compiler(m, silent=True, cse=cse, compiler_flags=flags)
+            if "libm" in v:
+                comp.libm = v["libm"]
+            art = comp.compile()
         except Exception as e:
             print(v, "compile failed", str(e)[:200])
             continue
