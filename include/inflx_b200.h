@@ -160,11 +160,17 @@ typedef struct {
   uint64_t row_begin;     /* rows [row_begin, row_end) are evaluated */
   uint64_t row_end;
   double aux;             /* accuracy of flag_quantum_dif, else unused */
-  void *out;              /* [n_vectors][row_end-row_begin][n1][k] (hesse: [n_vectors][4][rows][n1]) */
-  int out_is_device;      /* 1: `out` is device memory on `device` and stays there (no copy) */
+  void *out;              /* [n_vectors][row_end-row_begin][n1][k]; hesse, component-major:
+                             host output [n_vectors][4][rows][n1], device-resident output
+                             [4][n_vectors][rows][n1] */
+  int out_is_device;      /* 1: `out` is device memory on `device` and stays there (no copy);
+                             at most 65535 * (rows per CTA) rows per call */
   int device;             /* ordinal for out_is_device / single-device host calls; -1: shard
                              over the handle's devices */
-  void *stream;           /* CUstream to launch on when out_is_device (NULL: internal stream) */
+  void *stream;           /* CUstream to launch on when out_is_device (NULL: internal stream).
+                             With a stream the call returns without synchronising; later calls on
+                             the same device (any stream) are ordered after it by an event, and
+                             inflx_close waits for it */
 } inflx_grid_request;
 
 typedef struct {

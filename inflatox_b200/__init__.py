@@ -5,7 +5,8 @@
 `InflationModel`, `consistency_conditions` (`InflationCondition`, `GeneralisedAL`), `log_info`,
 `log_warn`.  The symbolic model builder (`InflationModelBuilder`, reference symbolic.py) is
 upstream of the hot path and is NOT re-implemented: build models with the reference package and
-hand them to `inflatox_b200.Compiler`, or load a pickled model with `InflationModel.load`.
+hand them to `inflatox_b200.Compiler` (the `inflatox` overlay assembled by
+`__graft_entry__.build()` does exactly that under the reference's own package name).
 """
 from .version import __abi_version__, __version__
 from .model import InflationModel
@@ -36,7 +37,7 @@ def __getattr__(name):
             raise ImportError(
                 "InflationModelBuilder is the reference package's symbolic front-end "
                 "(`pip install inflatox`); inflatox_b200 accelerates the numerical path and takes "
-                "its InflationModel objects (or InflationModel.load fixtures) as input"
+                "its InflationModel objects as input"
             ) from e
         return InflationModelBuilder
     raise AttributeError(name)

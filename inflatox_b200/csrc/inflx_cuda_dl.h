@@ -25,7 +25,8 @@
   X(cuStreamSynchronize) X(cuStreamDestroy) X(cuStreamWaitEvent) X(cuEventCreate)               \
   X(cuEventRecord) X(cuEventSynchronize) X(cuEventElapsedTime) X(cuEventDestroy)                \
   X(cuLaunchKernel) X(cuGetErrorString) X(cuGetErrorName) X(cuPointerGetAttribute)              \
-  X(cuMemGetInfo) X(cuMemHostRegister) X(cuMemHostUnregister)
+  X(cuMemGetInfo) X(cuMemHostRegister) X(cuMemHostUnregister) X(cuMemHostGetDevicePointer)    \
+  X(cuCtxGetCurrent)
 
 #define INFLX_NVRTC_FUNCS(X)                                                                    \
   X(nvrtcCreateProgram) X(nvrtcDestroyProgram) X(nvrtcCompileProgram) X(nvrtcGetProgramLogSize) \

@@ -154,6 +154,14 @@ struct DeviceState {
   std::mutex mu;  // one grid call at a time per device (scratch buffers are shared)
   DevBuf d_p, d_pc, d_rc, d_cc, d_xs, d_out[2];
   PinBuf stage[2];
+  // A call that ran on a CALLER's stream returns without synchronising; its kernels may still be
+  // reading the shared scratch (d_p, d_pc, d_rc, d_cc) and the module's __constant__ bank.
+  // ev_user marks its end: the next user of the scratch waits for it on its own stream.
+  CUevent ev_user = nullptr;
+  bool user_pending = false;
+  // scalar entry points: mapped page-locked scratch (inputs then outputs), one launch per call
+  void* h_scalar = nullptr;
+  CUdeviceptr d_scalar = 0;
   std::string name;
   int sm_count = 148;
 };
@@ -217,10 +225,21 @@ static inflx_status get_device(int ordinal, DeviceState** out) {
   CU_TRY(cu.p_cuEventCreate(&d->ev_t1, CU_EVENT_DEFAULT));
   CU_TRY(cu.p_cuEventCreate(&d->ev_g0, CU_EVENT_DEFAULT));
   CU_TRY(cu.p_cuEventCreate(&d->ev_g1, CU_EVENT_DEFAULT));
+  CU_TRY(cu.p_cuEventCreate(&d->ev_user, CU_EVENT_DISABLE_TIMING));
   *out = d.get();
   g_devices[ordinal] = std::move(d);
   return INFLX_OK;
 }
+
+// Order the stream `cs` (about to touch the device's shared scratch / a module's __constant__ bank)
+// after a previous call that was left running on a caller's stream.  dev->mu must be held.
+static inflx_status order_after_user_stream(CudaDriver& cu, DeviceState* dev, CUstream cs) {
+  if (!dev->user_pending) return INFLX_OK;
+  CU_TRY(cu.p_cuStreamWaitEvent(cs, dev->ev_user, 0));
+  return INFLX_OK;
+}
+static const size_t kScalarScratch = 32u << 10;  // bytes: first half inputs, second half outputs
+static const uint64_t kScalarMaxPoints = 64;
 
 // ---------------------------------------------------------------------------------------------
 // staged (pageable destination) copy-out: pinned staging buffer -> caller's array, in parallel
@@ -430,6 +449,7 @@ static inflx_status run_shard(inflx_lib* lib, const inflx_grid_request& rq, cons
     return st;
   const bool to_device = rq.out_is_device != 0;
   CUstream cs = (to_device && rq.stream) ? (CUstream)rq.stream : dev->compute;
+  if ((st = order_after_user_stream(cu, dev, cs))) return st;
 
   // (1) parameters -> P-frontier values of every vector of the shard
   if (P > 0) {
@@ -470,6 +490,12 @@ static inflx_status run_shard(inflx_lib* lib, const inflx_grid_request& rq, cons
     rows_chunk = std::max<uint64_t>(RPT, target / (n1 * opb));
     rows_chunk = std::min<uint64_t>(rows_chunk - rows_chunk % RPT, rows_total);
   }
+  if (to_device && rows_total > 65535ull * RPT)
+    // one launch covers the rows of a device-resident request (gridDim.y <= 65535 row tiles)
+    return fail(INFLX_ERR_SHAPE, fmt("a device-resident output is limited to %llu rows per call "
+                                     "(%llu requested): split the request by rows",
+                                     (unsigned long long)(65535ull * RPT),
+                                     (unsigned long long)rows_total));
   rows_chunk = std::min<uint64_t>(rows_chunk, 65535ull * RPT);
 
   const bool direct = !to_device && is_pinned_host(cu, rq.out);
@@ -627,8 +653,13 @@ static inflx_status run_shard(inflx_lib* lib, const inflx_grid_request& rq, cons
     if ((st = finish((int)(k & 1)))) return st;
     if ((st = finish((int)((k & 1) ^ 1)))) return st;
   }
-  if (!(to_device && rq.stream)) {
+  if (to_device && rq.stream) {
+    // asynchronous return: whoever uses this device's scratch next is ordered after this point
+    CU_TRY(cu.p_cuEventRecord(dev->ev_user, cs));
+    dev->user_pending = true;
+  } else {
     CU_TRY(cu.p_cuStreamSynchronize(cs));
+    dev->user_pending = false;  // cs waited for ev_user above, so that work has finished too
     float ms = 0;
     CU_TRY(cu.p_cuEventElapsedTime(&ms, dev->ev_t0, dev->ev_t1));
     res.kernel_ms = ms;
@@ -706,6 +737,7 @@ inflx_status inflx_nvrtc_compile(const char* source, const char* name, const cha
 
 // ---- artefact -------------------------------------------------------------------------------
 static inflx_status validate_basis_at_random(inflx_lib* lib);
+void inflx_close(inflx_lib* lib);
 
 inflx_status inflx_open(const char* lib_path, int check_basis, inflx_lib** out) {
   *out = nullptr;
@@ -741,6 +773,10 @@ inflx_status inflx_open(const char* lib_path, int check_basis, inflx_lib** out) 
   if (sizeof(FileHeader) + (size_t)h.n_groups * sizeof(GroupEntry) > lib->file.size())
     return fail(INFLX_ERR_IO, fmt("Could not load Inflatox Compilation Artefact (path: %s). "
                                   "Error: \"truncated artefact\"", lib_path));
+  if (h.rpt == 0 || h.rpt > 1024 || h.block == 0 || h.block > 1024 || (h.block & 31))
+    return fail(INFLX_ERR_IO, fmt("Could not load Inflatox Compilation Artefact (path: %s). "
+                                  "Error: \"corrupt header (rows per CTA %u, CTA width %u)\"",
+                                  lib_path, h.rpt, h.block));
   lib->groups.resize(h.n_groups);
   memcpy(lib->groups.data(), lib->file.data() + sizeof(FileHeader), h.n_groups * sizeof(GroupEntry));
   for (auto& g : lib->groups)
@@ -755,7 +791,11 @@ inflx_status inflx_open(const char* lib_path, int check_basis, inflx_lib** out) 
   lib->devices = default_devices();
   if (check_basis) {
     inflx_status st = validate_basis_at_random(lib.get());
-    if (st) return st;
+    if (st) {
+      const std::string why = g_last_error;
+      inflx_close(lib.release());  // unloads the modules the validation loaded
+      return fail(st, why);
+    }
   }
   *out = lib.release();
   return INFLX_OK;
@@ -770,6 +810,10 @@ void inflx_close(inflx_lib* lib) {
       if (get_device(kv.first.first, &dev) == INFLX_OK) {
         std::lock_guard<std::mutex> lk(dev->mu);
         cu.p_cuCtxSetCurrent(dev->ctx);
+        if (dev->user_pending) {  // a kernel of this module may still run on a caller's stream
+          cu.p_cuEventSynchronize(dev->ev_user);
+          dev->user_pending = false;
+        }
         cu.p_cuStreamSynchronize(dev->compute);
         cu.p_cuModuleUnload(kv.second->mod);
       }
@@ -885,6 +929,34 @@ inflx_status inflx_points_eval(inflx_lib* lib, int opi, const double* p, const d
   if ((st = get_fn(lib, gm, std::string("inflx_points_") + op.name, &fn))) return st;
   const uint32_t P = lib->hdr.n_params, NPF = ge->npf;
   CUstream cs = dev->compute;
+  if ((st = order_after_user_stream(cu, dev, cs))) return st;
+
+  // scalar fast path (calc_V / calc_H, reference src/lib.rs:309-339, 384-419): one launch; inputs
+  // and result live in mapped page-locked memory, so no copy is enqueued at all
+  const uint64_t opb_s = op.out_bytes, xs_at = (P + 1) & ~1u;
+  if ((opi == INFLX_OP_POTENTIAL || opi == INFLX_OP_HESSE) && n <= kScalarMaxPoints &&
+      (xs_at + 2 * n) * 8 <= kScalarScratch / 2 && n * opb_s <= kScalarScratch / 2) {
+    CUfunction sfn = nullptr;
+    if (get_fn(lib, gm, std::string("inflx_scalar_") + op.name, &sfn) == INFLX_OK) {
+      if (!dev->h_scalar) {
+        CU_TRY(cu.p_cuMemHostAlloc(&dev->h_scalar, kScalarScratch,
+                                   CU_MEMHOSTALLOC_PORTABLE | CU_MEMHOSTALLOC_DEVICEMAP));
+        CU_TRY(cu.p_cuMemHostGetDevicePointer(&dev->d_scalar, dev->h_scalar, 0));
+      }
+      double* in = static_cast<double*>(dev->h_scalar);
+      double* res = in + kScalarScratch / 16;
+      if (P) memcpy(in, p, P * 8);
+      memcpy(in + xs_at, xs, n * 16);
+      CUdeviceptr d_in = dev->d_scalar, d_res = dev->d_scalar + kScalarScratch / 2;
+      void* args[] = {&d_res, &d_in, &n};
+      if ((st = launch(cu, sfn, (unsigned)((n + 63) / 64), 1, 1, 64, cs, args))) return st;
+      CU_TRY(cu.p_cuStreamSynchronize(cs));
+      dev->user_pending = false;
+      memcpy(out, res, n * opb_s);
+      return INFLX_OK;
+    }
+    g_last_error.clear();  // artefact without scalar kernels: the general path below
+  }
   if (P) {
     if ((st = ensure_dev(cu, dev->d_p, P * 8))) return st;
     CU_TRY(cu.p_cuMemcpyHtoDAsync(dev->d_p.ptr, p, P * 8, cs));
@@ -907,6 +979,7 @@ inflx_status inflx_points_eval(inflx_lib* lib, int opi, const double* p, const d
     CU_TRY(cu.p_cuMemcpyDtoHAsync((char*)out + b * opb, dev->d_out[0].ptr, m * opb, cs));
     CU_TRY(cu.p_cuStreamSynchronize(cs));
   }
+  dev->user_pending = false;
   return INFLX_OK;
 }
 
@@ -1260,6 +1333,7 @@ inflx_status inflx_measure_fp64_peak(int device, int repeats, double* tflops_bes
   if (r != CUDA_SUCCESS) return fail(INFLX_ERR_CUDA, "cuModuleLoadData(peak kernel) failed");
   CUfunction fn = nullptr;
   CU_TRY(cu.p_cuModuleGetFunction(&fn, mod, "inflx_dfma_peak"));
+  if ((st = order_after_user_stream(cu, dev, dev->compute))) return st;
   if ((st = ensure_dev(cu, dev->d_p, 64))) return st;
   int sms = 0;
   cu.p_cuDeviceGetAttribute(&sms, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, dev->dev);
@@ -1353,10 +1427,25 @@ inflx_status inflx_host_free(void* ptr) {
       g_host_maps.erase(it);
     }
   }
+  // may run on any thread (a numpy view's finaliser): make a context current like inflx_host_alloc
+  CUcontext cur = nullptr;
+  if (cu.p_cuCtxGetCurrent(&cur) != CUDA_SUCCESS || !cur) {
+    DeviceState* dev = nullptr;
+    std::vector<int> d = default_devices();
+    inflx_status st = get_device(d.empty() ? 0 : d[0], &dev);
+    if (st) return st;
+    CU_TRY(cu.p_cuCtxSetCurrent(dev->ctx));
+  }
   if (len) {
     CUresult r = cu.p_cuMemHostUnregister(ptr);
+    if (r != CUDA_SUCCESS) {
+      // the driver still holds the registration: unmapping the pages under it would leave a
+      // dangling DMA mapping, so the block is kept (leaked) and the error reported
+      std::lock_guard<std::mutex> lk(g_host_mu);
+      g_host_maps[ptr] = len;
+      CU_TRY(r);
+    }
     munmap(ptr, len);
-    CU_TRY(r);
     return INFLX_OK;
   }
   CU_TRY(cu.p_cuMemFreeHost(ptr));

@@ -93,6 +93,10 @@ GROUPS = {
     "hes": (("v00", "v01", "v10", "v11"), (), ("hesse",), ("hesse",)),
 }
 
+# point ops that additionally get a one-launch scalar kernel (`inflx_scalar_<op>`)
+SCALAR_OPS = ("potential", "hesse")
+
+
 def _lit(v: float) -> str:
     if math.isnan(v):
         return "(0.0/0.0)"
@@ -146,9 +150,13 @@ class GroupProgram:
     parameter-class denominator costs 3 FP64 instructions instead of 9.
     """
 
-    def __init__(self, dag: Dag, roots: ModelRoots, group: str, n_params: int, libm: str = "glibc"):
+    def __init__(self, dag: Dag, roots: ModelRoots, group: str, n_params: int, libm: str = "glibc",
+                 cols: str = "auto"):
         if libm not in LIBM_FLAVOURS:
             raise Exception(f"unknown libm flavour {libm!r}: one of {LIBM_FLAVOURS}")
+        if cols not in ("auto", "always", "never"):
+            raise Exception(f"unknown column pre-pass mode {cols!r}: auto, always or never")
+        self.cols = cols
         self.dag = dag
         self.group = group
         self.n_params = n_params
@@ -277,6 +285,10 @@ class GroupProgram:
             self.klass(i) == "C" and self.node(i)[0] == "f" and self._hoisted_libm(i) is not None
             for i in self.grid_nodes
         )
+        if self.cols != "auto":
+            self.cols_prepass = self.cols == "always" and any(
+                self.klass(i) == "C" and self.is_op(i) for i in self.grid_nodes
+            )
         self.c_frontier = (
             [
                 i
@@ -496,6 +508,7 @@ class GroupProgram:
         src.append(f"#define INFLX_NP {self.n_params}\n#define INFLX_NPF {npf}\n")
         src.append(f"#define INFLX_NRF {nrf}\n#define INFLX_PC_CAP {PC_CAPACITY}\n")
         src.append(f"#define INFLX_NCF {len(self.c_frontier)}\n")
+        src.append(f"#define INFLX_SCALAR_XS {(self.n_params + 1) & ~1}\n")
         src.append("__constant__ double inflx_pc[INFLX_PC_CAP];\n\n")
 
         # ---- (1) parameter block: one thread per parameter vector ----
@@ -573,6 +586,8 @@ class GroupProgram:
         # ---- (4) point kernels (on-trajectory / scalar entry points) ----
         for op in self.point_ops:
             src.append(self._point_kernel(op))
+            if op in SCALAR_OPS:
+                src.append(self._scalar_kernel(op))
         return "".join(src)
 
     def _epilogue(self, op: str, val, point: str, indent: str, spec: bool) -> str:
@@ -725,12 +740,23 @@ class GroupProgram:
             + mixed
             + root_loads
             + self._epilogue(op, val, "point", "    ", spec_epi)
+            # INFLX_EARLY_STORE: the speculative result is stored as soon as it exists (its
+            # registers are free before the validity flag is final) and overwritten by the rare
+            # recomputation; otherwise one store after the flag is known
+            + "#ifdef INFLX_EARLY_STORE\n"
+            + self._store(op, "point", "    ")
+            + "#endif\n"
             + "    if (bad) {  // rare: redo this point with the IEEE operators\n"
             f"      double roots[{len(order)}];\n"
             "      inflx_slow_roots(rr, x1, pbase, roots);\n"
             + self._epilogue(op, slow_val, "point", "      ", False)
+            + "#ifdef INFLX_EARLY_STORE\n"
+            + self._store(op, "point", "      ")
+            + "#endif\n"
             + "    }\n"
+            + "#ifndef INFLX_EARLY_STORE\n"
             + self._store(op, "point", "    ")
+            + "#endif\n"
             + "  }\n}\n\n"
         )
 
@@ -775,6 +801,42 @@ class GroupProgram:
             "  (void)x0; (void)x1; (void)aux;\n" + body + epi + "}\n\n"
         )
 
+    def _scalar_kernel(self, op: str) -> str:
+        """The scalar entry points `potential(x, p)` / `hesse(x, p)` (reference src/lib.rs:309-339,
+        384-419) as ONE launch: every class of the group - parameter block included - evaluated
+        inline by the thread, parameters and coordinates read from, and the result written to,
+        mapped page-locked host memory.  The general path costs H2D + inflx_params + DtoD into
+        __constant__ + H2D + inflx_points_* + D2H per call; this one a launch and a stream
+        synchronise.  Same operations, same libm flavour per node class as the two-kernel path, so
+        the values are bit-identical to inflx_points_<op>."""
+        scope = self._leaf_scope(
+            {("p", k): f"p[{k}]" for k in range(self.n_params)} | {("x", 0): "x0", ("x", 1): "x1"}
+        )
+        roots = self.grid_roots
+        nodes = [
+            i for i in self.dag.reachable(list(roots.values()))
+            if self.is_op(i) and self.klass(i) in "PRCM"
+        ]
+        body = self._block(nodes, scope, "  ", spec=False)
+
+        def val(rname: str) -> str:
+            return self._ref(roots[rname], scope)
+
+        if op == "hesse":
+            epi = "  double o4[4];\n" + self._epilogue(op, val, "k", "  ", False)
+            epi += "".join(f"  out[k * 4 + {c}] = o4[{c}];\n" for c in range(4))
+        else:
+            epi = "  double o1;\n" + self._epilogue(op, val, "k", "  ", False) + "  out[k] = o1;\n"
+        return (
+            f"extern \"C\" __global__ void inflx_scalar_{op}(double* __restrict__ out, "
+            "const double* __restrict__ in, u64 n) {\n"
+            "  const u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;\n"
+            "  if (k >= n) return;\n"
+            "  const double* __restrict__ p = in;\n"
+            "  const double x0 = in[INFLX_SCALAR_XS + 2 * k], x1 = in[INFLX_SCALAR_XS + 2 * k + 1];\n"
+            "  (void)p; (void)x0; (void)x1;\n" + body + epi + "}\n\n"
+        )
+
     def _inner_function(self) -> str:
         """`inner_prod` (reference compiler.py:445-472) as a device function of the two vectors."""
         scope = {n: f"inflx_pc[{k}]" for n, k in self.p_slot.items()}
@@ -800,7 +862,7 @@ class GroupProgram:
 class ModelProgram:
     """All groups of one model + the metadata the artefact header carries."""
 
-    def __init__(self, unit: ParsedUnit, libm: str = "glibc"):
+    def __init__(self, unit: ParsedUnit, libm: str = "glibc", cols: str = "auto"):
         self.libm = libm
         if unit.dim != 2:
             raise Exception(
@@ -809,7 +871,8 @@ class ModelProgram:
         self.unit = unit
         self.roots = ModelRoots(unit)
         self.groups = {
-            g: GroupProgram(unit.dag, self.roots, g, unit.n_parameters or 0, libm) for g in GROUPS
+            g: GroupProgram(unit.dag, self.roots, g, unit.n_parameters or 0, libm, cols)
+            for g in GROUPS
         }
 
     def flops_per_point(self, op: str) -> int:

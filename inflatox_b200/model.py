@@ -5,13 +5,12 @@ the reference's container (reference python/inflatox/symbolic.py:30-88) so that 
 the reference's unchanged `InflationModelBuilder` can be handed to `inflatox_b200.Compiler`
 directly (duck typing: only the attributes below are read).  The symbolic derivation itself
 (Christoffels, covariant Hesse, vielbein projection; symbolic.py:287-726) is upstream of the hot
-path and out of scope; models are either produced by the reference package or
-loaded from a pickled fixture with `InflationModel.load`.
+path and out of scope: models are produced by the reference package (the
+`inflatox` overlay `__graft_entry__.build()` assembles runs the reference's unmodified
+`symbolic.py` on top of this back-end).  The test fixtures under tests/golden/models are such
+models, pickled; their loader lives in tests/cases.py, not here.
 """
 from __future__ import annotations
-
-import gzip
-import pickle
 
 import sympy
 
@@ -62,22 +61,6 @@ class InflationModel:
         "model_name", "coordinates", "tangents", "basis", "eom_fields", "eom_h", "eom_hdot",
         "potential", "metric", "gradient_square", "hesse_cmp",
     )  # fmt: skip
-
-    def to_dict(self) -> dict:
-        d = {k: getattr(self, k) for k in self.FIELDS if k != "tangents"}
-        d["tangents"] = self.coordinate_tangents
-        return d
-
-    def save(self, path: str) -> None:
-        with gzip.GzipFile(path, "wb", mtime=0) as fh:
-            pickle.dump(self.to_dict(), fh, protocol=4)
-
-    @classmethod
-    def load(cls, path: str) -> "InflationModel":
-        """Load a model pickled by `save` / tests/golden/make_golden.py (dict of sympy objects)."""
-        with gzip.open(path, "rb") as fh:
-            d = pickle.load(fh)
-        return cls(**{k: d[k] for k in cls.FIELDS})
 
     def __str__(self):
         return (

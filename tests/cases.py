@@ -41,6 +41,21 @@ def golden_cse(model: str) -> bool:
         return bool(json.load(fh)["cse"])
 
 
+def load_model(model: str):
+    """The symbolic model of one of the reference's tests, built by the reference's own
+    `InflationModelBuilder` and pickled by tests/golden/make_golden.py (a dict of sympy
+    expressions).  TEST FIXTURE LOADER: unpickling executes code, so this lives under tests/ and
+    only ever reads the files committed under tests/golden/models/."""
+    import gzip
+    import pickle
+
+    import inflatox_b200 as ix
+
+    with gzip.open(os.path.join(GOLDEN, "models", f"{model}.pkl.gz"), "rb") as fh:
+        d = pickle.load(fh)
+    return ix.InflationModel(**{k: d[k] for k in ix.InflationModel.FIELDS})
+
+
 @functools.lru_cache(maxsize=None)
 def artifact(model: str, fmad: bool = False, libm: str | None = None):
     """Compile the pickled reference-built model with inflatox_b200.Compiler (cached per process;
@@ -48,7 +63,7 @@ def artifact(model: str, fmad: bool = False, libm: str | None = None):
     calls (cudagen.LIBM_FLAVOURS), default = the Compiler's."""
     import inflatox_b200 as ix
 
-    m = ix.InflationModel.load(os.path.join(GOLDEN, "models", f"{model}.pkl.gz"))
+    m = load_model(model)
     flags = None
     if fmad:
         flags = [f.replace("--fmad=false", "--fmad=true") for f in ix.Compiler.default_nvrtc_flags]

@@ -90,7 +90,7 @@ def test_generated_c_equals_the_references_output(model):
     produced for the same symbolic model (fixture: tests/golden/c, made by make_golden.py).  The
     eom* functions are excluded: they are off the path, and sympy re-distributes their leading
     -1/2 when the model fixture is un-pickled."""
-    m = ix.InflationModel.load(os.path.join(cases.GOLDEN, "models", f"{model}.pkl.gz"))
+    m = cases.load_model(model)
     meta = oracle.golden_meta(model)
     comp = ix.Compiler(m, silent=True, cse=meta["cse"])
     mine, gold = _functions(comp._generate_c_source()), _functions(oracle.golden_c_text(model))
@@ -119,7 +119,7 @@ def test_compile_produces_a_cuda_artefact():
 
 
 def test_artifact_is_removed_with_auto_cleanup():
-    m = ix.InflationModel.load(os.path.join(cases.GOLDEN, "models", "doc.pkl.gz"))
+    m = cases.load_model("doc")
     art = ix.Compiler(m, silent=True, cleanup=True).compile()
     path = art.shared_object_path
     assert os.path.exists(path)
@@ -128,7 +128,7 @@ def test_artifact_is_removed_with_auto_cleanup():
 
 
 def test_gsl_special_functions_are_rejected_at_compile_time():
-    m = ix.InflationModel.load(os.path.join(cases.GOLDEN, "models", "doc.pkl.gz"))
+    m = cases.load_model("doc")
     r = m.coordinates[0]
     m.potential = m.potential + sympy.besselj(0, r)
     with pytest.raises(UnsupportedFunctionError, match="no fp64 device implementation"):
@@ -153,7 +153,7 @@ def test_flops_per_point_are_frozen():
 def test_piecewise_models_compile():
     """sympy prints Piecewise / sign / Heaviside as (multi-line) C conditionals; the parser, the
     DAG and the CUDA emitter carry them (cmp / and / or / not / sel nodes)."""
-    m = ix.InflationModel.load(os.path.join(cases.GOLDEN, "models", "doc.pkl.gz"))
+    m = cases.load_model("doc")
     r, th = m.coordinates
     m.potential = m.potential + sympy.Piecewise((r**2, r > 1), (sympy.sign(th) * th, True))
     comp = ix.Compiler(m, silent=True)

@@ -22,7 +22,7 @@ from inflatox_b200 import libinflx_rs as rs
 def main():
     model, op, n = sys.argv[1], sys.argv[2], int(sys.argv[3])
     variants = json.loads(sys.argv[4]) if len(sys.argv) > 4 else None
-    m = ix.InflationModel.load(os.path.join(cases.GOLDEN, "models", f"{model}.pkl.gz"))
+    m = cases.load_model(model)
     cse = cases.golden_cse(model)
     per = 6 if op == "complete_analysis" else 1
     d = torch.empty(n * n * per, dtype=torch.float64, device="cuda:0")
@@ -40,6 +40,8 @@ def main():
             comp = ix.Compiler(m, silent=True, cse=cse, compiler_flags=flags)
             if "libm" in v:
                 comp.libm = v["libm"]
+            if "cols" in v:
+                comp.cols_prepass = v["cols"]
             art = comp.compile()
         except Exception as e:
             print(v, "compile failed", str(e)[:200])
