@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """bench.py - throughput of the grid-evaluation hot path (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W [--config C1..C5] [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--config C1..C8] [--no-all] [--impl reference]
 
 A "step" is one pass of the hot path over the configured grid.  Default workload: BASELINE
 config C3 (EGNO model, complete_analysis, 16384 x 16384 grid, rows sharded over the N ranks - the
@@ -21,8 +21,18 @@ torch.distributed traffic is the barrier and the max-over-ranks of the timings.
     cpu_baseline  the oracle (restated reference path, gcc + OpenMP over all host cores) timed on
                a bounded row sample of the same grid (N=1, rank 0)
 
+    configs    (N=1, unless --no-all) the same device-resident measurement + rooflines for every
+               other BASELINE config and for complete_analysis on a 16384^2 grid of each remaining
+               repo test model (C6 angular, C7 hyper, C8 doc): north_star's ">= 50 % of the FP64
+               roofline for each repo test model" is judged on these
+    e2e_inprocess  (N>1) the ONE call a user of the reference makes - GeneralisedAL.
+               complete_analysis - in ONE process driving all N GPUs (rank 0; the engine's own
+               thread-per-device row sharding), next to the one-process-per-GPU figure in `e2e`
+
 --impl reference times that same CPU path as the reference arm (the reference's Rust crate cannot
-be built here: no rustc/cargo).
+be built here: no rustc/cargo).  The CPU legs time the -ffp-contract=fast build of
+the reference-generated C (the reference ships clang, which contracts by default; gcc's `fast`
+contracts at least as much), i.e. the FASTER of the two CPU builds; parity uses the `off` build.
 """
 from __future__ import annotations
 
@@ -48,8 +58,17 @@ CONFIGS = {
     "C3": ("egno", "complete_analysis", 16384, 16384, 1),
     "C4": ("d5", "complete_analysis", 16384, 16384, 1),
     "C5": ("hyper", "complete_analysis", 1024, 1024, 1024),
+    # north_star: "complete_analysis on a 16384^2 grid for each repo test model" (C3 = EGNO and
+    # C4 = d5 are BASELINE configs already)
+    "C6": ("angular", "complete_analysis", 16384, 16384, 1),
+    "C7": ("hyper", "complete_analysis", 16384, 16384, 1),
+    "C8": ("doc", "complete_analysis", 16384, 16384, 1),
 }
 OUT_DOUBLES = {"complete_analysis": 6, "consistency_only": 1}
+# contraction mode of the CPU legs' build of the reference-generated C (see module docstring)
+CPU_CONTRACT = "fast"
+CPU_BUILD = ("gcc -O3 -march=native -fno-math-errno -fno-signed-zeros -ffp-contract=fast "
+             "(the reference's flag set, compiler.py:299-310; contraction as clang's default)")
 
 
 def workload(cfg: str):
@@ -135,7 +154,7 @@ def cpu_rate(model, op, n0, n1, ext, p, seconds, threads=0):
     """points/s of the restated reference CPU path on a bounded row sample (~`seconds`)."""
     import oracle
 
-    orc = oracle.Oracle(model)
+    orc = oracle.Oracle(model, contract=CPU_CONTRACT)
     fn = getattr(orc, op)
     threads = threads or (os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1: be explicit
     probe_rows = max(1, min(n0, (1 << 20) // n1))
@@ -165,7 +184,8 @@ def run_reference(a, out):
     pts = sum(x for x, _ in per_step)
     tt = sum(t for _, t in per_step)
     value = pts / tt
-    sample = f"rows [{r0},{r0 + rows}) of the {n0}x{n1} grid per step ({rows * n1} points)"
+    sample = (f"rows [{r0},{r0 + rows}) of the {n0}x{n1} grid per step ({rows * n1} points); "
+              f"restated reference path, {CPU_BUILD} + OpenMP over all cores")
     line = {
         "impl": "reference", "metric": "grid_points_per_s", "value": value, "unit": "points/s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
@@ -216,6 +236,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU baseline sample size")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-all", action="store_true",
+                    help="skip the per-config device-resident lines under `configs` (N=1)")
     a = ap.parse_args()
     out = _claim_stdout()
     if a.impl == "reference":
@@ -330,6 +352,9 @@ def main():
     roofline = {
         "bound": "fp64", "kernel": f"inflx_grid_{op}", "achieved": achieved_tf, "peak": fp64_peak,
         "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak, "traffic": traffic,
+        "traffic_source": None if traffic is None else "profiles/ncu_traffic.json: dram bytes of one "
+        "`ncu --set full` capture of this kernel (committed, scaled to this rank's shard) - NOT "
+        "measured in this run",
         "flops_per_point": F, "points_per_launch": my_points,
         "peak_source": "DFMA micro-kernel measured in this run (inflx_measure_fp64_peak; "
         f"median {med.value:.2f}); MEASURED_PEAKS.json has no fp64 entry",
@@ -390,8 +415,80 @@ def main():
         cpu = {
             "value": rate, "unit": "points/s", "cores": os.cpu_count(), "kind": "port",
             "sample": f"rows [{rr0},{rr0 + rows}) of the {n0}x{n1} grid ({rows * n1} points, "
-            f"{dt:.1f} s), restated reference path (gcc -O3 -march=native + OpenMP, all cores)",
+            f"{dt:.1f} s), restated reference path, {CPU_BUILD} + OpenMP over all cores",
         }  # fmt: skip
+
+    # ---- every other config, device-resident + rooflines (N=1) -------------------------------------
+    def device_only(cfg: str, steps: int, warmup: int) -> dict:
+        c_model, c_op, c_n0, c_n1, c_S, c_ext, c_p = workload(cfg)
+        c_art = cases.artifact(c_model)
+        c_lib = rs.open_inflx_dylib(c_art.shared_object_path, False)
+        c_lib.set_devices([local])
+        c_per, c_F = OUT_DOUBLES[c_op], c_art.flops_per_point(c_op)
+        pts = c_S * c_n0 * c_n1
+        buf = torch.empty(pts * c_per, dtype=torch.float64, device="cuda")
+        fl = torch.empty(1 << 28, dtype=torch.uint8, device="cuda") if pts * c_per * 8 <= (1 << 28) else None
+        c_ss = np.array(c_ext, dtype=np.float64)
+        t_all = t_grid = 0.0
+        for i in range(warmup + steps):
+            if fl is not None:
+                fl.fill_(1)
+                torch.cuda.synchronize()
+            r = rs.grid_eval(c_lib, c_op, c_p, None, c_n0, c_n1, c_ss, device=local,
+                             out_device_ptr=buf.data_ptr())  # fmt: skip
+            if i >= warmup:
+                t_all += r["kernel_ms"]
+                t_grid += r["grid_ms"]
+        del buf, fl
+        torch.cuda.empty_cache()
+        tf = c_F * pts / (t_grid / steps / 1e3) / 1e12
+        gbs = pts * c_per * 8 / (t_grid / steps / 1e3) / 1e9
+        return {
+            "workload": config_dict(cfg, c_model, c_op, c_n0, c_n1, c_S, 1)["workload"],
+            "value": pts * steps / (t_all / 1e3), "unit": "points/s", "steps": steps,
+            "ms_per_step": t_all / steps, "dominant_kernel_ms_per_step": t_grid / steps,
+            "roofline": {"bound": "fp64", "kernel": f"inflx_grid_{c_op}", "achieved": tf,
+                         "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
+                         "flops_per_point": c_F},
+            "roofline_hbm": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": gbs / hbm_peak, "bytes_per_point": c_per * 8},
+        }  # fmt: skip
+
+    configs = None
+    if rank == 0 and world == 1 and not a.no_all:
+        configs = {}
+        for cfg in sorted(CONFIGS):
+            if cfg != a.config:
+                configs[cfg] = device_only(cfg, max(3, min(a.steps, 10)), 3)
+
+    # ---- N > 1: the one facade call a user makes, ONE process driving all N GPUs (rank 0) ---------
+    e2e_inprocess = None
+    if world > 1 and S == 1 and not a.no_e2e:
+        barrier()
+        if rank == 0:
+            from inflatox_b200.consistency_conditions import GeneralisedAL
+
+            al = GeneralisedAL(art)
+            al.dylib.set_devices(list(range(world)))
+            call = al.complete_analysis if op == "complete_analysis" else al.consistency
+            k_steps = max(2, min(a.steps, 5))
+            times = []
+            for i in range(3 + k_steps):  # the first calls pin the pooled output block
+                t0 = time.perf_counter()
+                res = call(p[0], *ext, n0, n1, progress=False)
+                dt = time.perf_counter() - t0
+                del res
+                if i >= 3:
+                    times.append(dt)
+            e2e_inprocess = {
+                "value": total_points * len(times) / sum(times), "unit": "points/s",
+                "ms_per_step": 1e3 * sum(times) / len(times), "steps": len(times),
+                "n_devices": world, "d2h_bytes_per_step": int(total_points * per * 8),
+                "api": "GeneralisedAL." + call.__name__ + "(args, x0_start, x0_stop, x1_start, "
+                "x1_stop, N_x0, N_x1) in one process, lib.set_devices(range(N)): one host thread "
+                "per device, row shards written by DMA into the one pinned numpy output",
+            }
+        barrier()
 
     if rank == 0:
         line = {
@@ -405,6 +502,10 @@ def main():
             "dominant_kernel_ms_per_step": grid_ms_max / a.steps,
             "per_rank_ms_per_step": per_rank_ms, "per_rank_dominant_kernel_ms": per_rank_grid_ms,
         }  # fmt: skip
+        if configs is not None:
+            line["configs"] = configs
+        if e2e_inprocess is not None:
+            line["e2e_inprocess"] = e2e_inprocess
         print(json.dumps(line), file=out, flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -66,6 +66,9 @@ const char *inflx_last_error(void);
 inflx_status inflx_nvrtc_compile(const char *source, const char *name, const char *const *options,
                                  int n_options, void **cubin, size_t *cubin_size, char **log);
 void inflx_free(void *ptr);
+/* NVRTC version (part of the cubin cache key of inflatox_b200.Compiler); INFLX_ERR_NVRTC and
+ * 0.0 when NVRTC cannot be loaded. */
+inflx_status inflx_nvrtc_version(int *major, int *minor);
 
 /* ---- artefact handle ------------------------------------------------------------------------ */
 /* open_inflx_dylib(lib_path, check_basis) (reference src/lib.rs:108-115; loader src/dylib.rs:67-161,

@@ -118,6 +118,7 @@ def _declare(lib: ctypes.CDLL) -> None:
         c.c_char_p, c.c_char_p, c.POINTER(c.c_char_p), ci, c.POINTER(vp), c.POINTER(sz),
         c.POINTER(vp),
     ]  # fmt: skip
+    lib.inflx_nvrtc_version.argtypes = [c.POINTER(ci), c.POINTER(ci)]
     lib.inflx_set_devices.argtypes = [vp, c.POINTER(ci), ci]
     lib.inflx_get_devices.argtypes = [vp, c.POINTER(ci), ci]
     lib.inflx_complete_analysis.argtypes = [vp, dp, sz, dp, sz, sz, sz, dp, sz, sz, ci, sz]

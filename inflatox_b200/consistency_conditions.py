@@ -64,13 +64,36 @@ class InflationCondition:
         """Projected Hesse matrix [[v00, v01], [v10, v11]] at `x`."""
         return self.dylib.hesse(x, args)
 
-    def calc_H_array(self, args, start, stop, N=None) -> np.ndarray:
-        """Projected Hesse matrix on a regular grid; result has shape (n, n, *N).  (The
-        reference's wrapper passes `np.array(n_fields)` instead of `N` and its Rust side asserts
-        `p.len() == n_fields` - consistency_conditions.py:156, src/hesse_bindings.rs:163 - so the
-        call fails upstream; here it does what its docstring promises.)"""
+    def calc_H_array(
+        self,
+        args,
+        x0_start,
+        x0_stop,
+        x1_start=None,
+        x1_stop=None,
+        N=None,
+    ) -> np.ndarray:
+        """Projected Hesse matrix on a regular grid; result has shape (2, 2, *N).
+
+        Signature of the reference (consistency_conditions.py:119-127): `(args, x0_start, x0_stop,
+        x1_start, x1_stop, N=None)`.  Upstream the call cannot succeed - the wrapper passes
+        `np.array(n_fields)` instead of `N` and the Rust side asserts `p.len() == n_fields`
+        (consistency_conditions.py:156, src/hesse_bindings.rs:163) - so only those two bugs are
+        fixed here.  As an extra, the list style of `calc_V_array` is accepted too:
+        `calc_H_array(args, start, stop, N)` with `start` / `stop` sequences."""
         n_fields = self.artifact.n_fields
-        start_stop = np.array([[float(a), float(b)] for (a, b) in zip(start, stop)])
+        if np.ndim(x0_start) > 0:  # (args, start, stop[, N]) - `x1_start` then carries N
+            if x1_stop is not None:
+                raise TypeError("calc_H_array(args, start, stop, N): too many positional arguments")
+            start, stop = x0_start, x0_stop
+            N = x1_start if N is None else N
+            start_stop = np.array([[float(a), float(b)] for (a, b) in zip(start, stop)])
+        else:
+            if x1_start is None or x1_stop is None:
+                raise TypeError("calc_H_array() missing required arguments: 'x1_start', 'x1_stop'")
+            start_stop = np.array(
+                [[float(x0_start), float(x0_stop)], [float(x1_start), float(x1_stop)]]
+            )
         N = N if N is not None else [8000 for _ in range(n_fields)]
         return self.dylib.hesse_array(
             np.array(N, dtype=np.int64), np.asarray(args, dtype=float), start_stop

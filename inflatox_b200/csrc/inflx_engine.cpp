@@ -735,6 +735,15 @@ inflx_status inflx_nvrtc_compile(const char* source, const char* name, const cha
   return INFLX_OK;
 }
 
+inflx_status inflx_nvrtc_version(int* major, int* minor) {
+  *major = *minor = 0;
+  Nvrtc& rt = Nvrtc::get();
+  if (!rt.ok) return fail(INFLX_ERR_NVRTC, rt.error);
+  if (rt.p_nvrtcVersion(major, minor) != NVRTC_SUCCESS)
+    return fail(INFLX_ERR_NVRTC, "nvrtcVersion failed");
+  return INFLX_OK;
+}
+
 // ---- artefact -------------------------------------------------------------------------------
 static inflx_status validate_basis_at_random(inflx_lib* lib);
 void inflx_close(inflx_lib* lib);

@@ -40,9 +40,16 @@ from .cexpr import Dag, ParsedUnit
 _CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 
 # resident CTAs per SM the register allocation of a group's grid kernels must allow (128-thread
-# CTAs: 5 -> 96 registers, 6 -> 80).  From the tools/tune.py sweeps over the five test models: the
-# six-output kernels are fastest at 6, the single-plane ones at 5.
+# CTAs: 4 -> 128 registers, 5 -> 96, 6 -> 80).  From the tools/tune.py sweeps over the five test
+# models: the six-output kernels are fastest at 6, the single-plane ones at 5 - unless the model
+# keeps many column-class values live across the row loop (2 registers each for the whole loop):
+# then the cap spills them to local memory, 6 CTAs x 128 threads x 200 B no longer fit L1 and the
+# reloads stall (angular: 27 values, 224 B of stack at 80 registers; tools/ab.py round 2:
+# complete_analysis 16384^2 6.18 -> 5.88 ms at 4 CTAs/SM, consistency_only 4096^2 0.249 -> 0.242).
+# `GroupProgram.min_blocks` lowers the count until 2 * (live column values) + WORKING_REGS fits.
 MIN_BLOCKS = {"cmp": 6, "hes": 6}
+REGS_AT = {6: 80, 5: 96, 4: 128}
+WORKING_REGS = 48
 PC_CAPACITY = 7680  # doubles of __constant__ memory for P-frontier values (60 of the 64 KiB)
 MAX_FAST_POW = 64  # |exponent| up to which literal (half-)integer powers use the dd chains
 # libm flavours for the model's libm calls in the hoisted node classes P / R / C (a column block
@@ -289,20 +296,21 @@ class GroupProgram:
             self.cols_prepass = self.cols == "always" and any(
                 self.klass(i) == "C" and self.is_op(i) for i in self.grid_nodes
             )
-        self.c_frontier = (
-            [
-                i
-                for i in self.grid_nodes
-                if self.klass(i) == "C"
-                and self.is_op(i)
-                and (
-                    i in grid_root_ids
-                    or any(u in grid_set and self.klass(u) != "C" for u in users.get(i, ()))
-                )
-            ]
-            if self.cols_prepass
-            else []
-        )
+        # column-class values the per-point code reads: live in registers over the whole row loop
+        self.c_live = [
+            i
+            for i in self.grid_nodes
+            if self.klass(i) == "C"
+            and self.is_op(i)
+            and (
+                i in grid_root_ids
+                or any(u in grid_set and self.klass(u) != "C" for u in users.get(i, ()))
+            )
+        ]
+        self.c_frontier = self.c_live if self.cols_prepass else []
+        self.min_blocks = MIN_BLOCKS.get(self.group, 5)
+        while self.min_blocks > 4 and 2 * len(self.c_live) + WORKING_REGS > REGS_AT[self.min_blocks]:
+            self.min_blocks -= 1
         self.c_slot = {n: k for k, n in enumerate(self.c_frontier)}
         # rows of the row-frontier array are read with 128-bit loads: keep them 16-byte aligned
         self.n_row_slots = (len(self.r_frontier) + 1) & ~1
@@ -371,6 +379,8 @@ class GroupProgram:
             "n_r_frontier": len(self.r_frontier),
             "n_row_slots": self.n_row_slots,
             "n_c_frontier": len(self.c_frontier),
+            "n_c_live": len(self.c_live),
+            "min_blocks": self.min_blocks,
         }
 
     # -- emission ----------------------------------------------------------------------------
@@ -503,7 +513,7 @@ class GroupProgram:
             with open(os.path.join(_CSRC, "inflx_glibcmath.cuh")) as fh:
                 device_header += "\n" + fh.read().replace('#include "inflx_glibc_tables.cuh"', tables)
         npf, nrf = len(self.p_frontier), self.n_row_slots
-        src = [f"#define INFLX_GROUP_MIN_BLOCKS {MIN_BLOCKS.get(self.group, 5)}\n", device_header]
+        src = [f"#define INFLX_GROUP_MIN_BLOCKS {self.min_blocks}\n", device_header]
         src.append(f'\n// ===== generated: model "{model_name}", group "{self.group}" =====\n')
         src.append(f"#define INFLX_NP {self.n_params}\n#define INFLX_NPF {npf}\n")
         src.append(f"#define INFLX_NRF {nrf}\n#define INFLX_PC_CAP {PC_CAPACITY}\n")
@@ -718,7 +728,7 @@ class GroupProgram:
             "#endif\n"
             "  const bool active = col < n1;\n"
             "  const double x1 = inflx_coord(active ? col : 0u, dx1, of1);\n"
-            "  bool bad_c = false;\n"
+            "  inflx_chk bad_c;\n"
             "  (void)x1; (void)aux; (void)comp_stride; (void)rc; (void)pbase; (void)cc;\n"
             + col_block
             + "#if INFLX_NRF > 0\n  __syncthreads();\n#endif\n"
@@ -734,27 +744,27 @@ class GroupProgram:
             "    const double2* __restrict__ rr = nullptr;\n"
             "#endif\n"
             "    const u64 point = rowid * n1 + col;\n"
-            "    bool bad = bad_c;\n"
+            "    inflx_chk bad = bad_c;\n"
             f"    {decl}\n"
             "    (void)rr;\n"
             + mixed
             + root_loads
             + self._epilogue(op, val, "point", "    ", spec_epi)
-            # INFLX_EARLY_STORE: the speculative result is stored as soon as it exists (its
-            # registers are free before the validity flag is final) and overwritten by the rare
-            # recomputation; otherwise one store after the flag is known
-            + "#ifdef INFLX_EARLY_STORE\n"
+            # the speculative result is stored as soon as it exists (its registers are free before
+            # the validity flag is final) and overwritten by the rare recomputation;
+            # -DINFLX_LATE_STORE: one store after the flag is known (round 1)
+            + "#ifndef INFLX_LATE_STORE\n"
             + self._store(op, "point", "    ")
             + "#endif\n"
-            + "    if (bad) {  // rare: redo this point with the IEEE operators\n"
+            + "    if (bad.any()) {  // rare: redo this point with the IEEE operators\n"
             f"      double roots[{len(order)}];\n"
             "      inflx_slow_roots(rr, x1, pbase, roots);\n"
             + self._epilogue(op, slow_val, "point", "      ", False)
-            + "#ifdef INFLX_EARLY_STORE\n"
+            + "#ifndef INFLX_LATE_STORE\n"
             + self._store(op, "point", "      ")
             + "#endif\n"
             + "    }\n"
-            + "#ifndef INFLX_EARLY_STORE\n"
+            + "#ifdef INFLX_LATE_STORE\n"
             + self._store(op, "point", "    ")
             + "#endif\n"
             + "  }\n}\n\n"

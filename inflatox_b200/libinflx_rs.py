@@ -535,8 +535,12 @@ def grid_eval(lib, op: str, p, out, n0: int, n1: int, start_stop, rows=None, acc
     else:
         per = {"complete_analysis": 6, "hesse": 4}.get(op, 1)
         need = p2.shape[0] * (r1 - r0) * n1 * per
-        if not isinstance(out, np.ndarray) or not out.flags.c_contiguous or out.size != need:
-            raise TypeError(f"out must be a C-contiguous array of {need} elements")
+        want = np.bool_ if op == "flag_quantum_dif" else np.float64
+        if (not isinstance(out, np.ndarray) or not out.flags.c_contiguous or out.size != need
+                or out.dtype != want or not out.flags.writeable):  # fmt: skip
+            raise TypeError(
+                f"out must be a writeable C-contiguous {np.dtype(want).name} array of {need} elements"
+            )
         rq.out = out.ctypes.data_as(ctypes.c_void_p)
         rq.out_is_device = 0
     rq.device = device

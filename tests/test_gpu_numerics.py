@@ -9,17 +9,17 @@ extern "C" __global__ void t_div(const double* a, const double* b, double* q, do
                                  unsigned char* bad, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  bool f = false;
+  inflx_chk f;
   q[i] = inflx_div_s(a[i], b[i], f);
-  bad[i] = f;
+  bad[i] = f.any();
   qe[i] = a[i] / b[i];
 }
 extern "C" __global__ void t_sqrt(const double* a, double* q, double* qe, unsigned char* bad, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  bool f = false;
+  inflx_chk f;
   q[i] = inflx_sqrt_s(a[i], f);
-  bad[i] = f;
+  bad[i] = f.any();
   qe[i] = sqrt(a[i]);
 }
 extern "C" __global__ void t_pow(const double* a, double* p3, double* p4, double* p7, double* pm2,
@@ -97,11 +97,13 @@ def test_speculative_sqrt_is_ieee_whenever_it_claims_so(mod):
     assert _same(q[ok], qe[ok]).all()
     m = (a > 1e-100) & (a < 1e100)
     assert (bad[m] == 0).all()
-    # zero, inf, -0 need the slow path; a negative or NaN argument is NaN on the fast path too
-    assert bad[0] == 1 and bad[1] == 1 and bad[3] == 1
-    assert bad[2] == 0 and bad[5] == 0 and bad[7] == 0 and np.isnan(q[[2, 5, 7]]).all()
-    neg = a < -1e-300
-    assert (bad[neg] == 0).all() and np.isnan(q[neg]).all()
+    # zero, inf, -0 and NaN take the slow path (a NaN argument means a NaN upstream, whose quotients
+    # have flagged the point anyway); a negative argument of ordinary magnitude is NaN on the fast
+    # path too and must NOT be flagged (omega / eta are NaN by design on 10-60 % of a grid)
+    assert bad[0] == 1 and bad[1] == 1 and bad[2] == 1 and bad[3] == 1
+    assert bad[5] == 0 and np.isnan(q[[2, 5, 7]]).all()
+    neg = (a < -1e-290) & np.isfinite(a)
+    assert neg.sum() > 1000 and (bad[neg] == 0).all() and np.isnan(q[neg]).all()
 
 
 def test_double_double_powers_are_correctly_rounded(mod):
