@@ -469,7 +469,16 @@ def main():
             from inflatox_b200.consistency_conditions import GeneralisedAL
 
             al = GeneralisedAL(art)
+            # the in-process sharding changes no bit: a ragged grid on one device vs on all of them
+            # (tests/test_gpu_parity.py::test_multi_device_row_sharding_in_one_process, which a
+            # 1-GPU test box has to skip, executed here where N devices exist)
+            al.dylib.set_devices([0])
+            one = np.zeros((203, 157, 6))
+            rs.grid_eval(al.dylib, "complete_analysis", p[0], one, 203, 157, ss)
             al.dylib.set_devices(list(range(world)))
+            many = np.zeros((203, 157, 6))
+            rep_many = rs.grid_eval(al.dylib, "complete_analysis", p[0], many, 203, 157, ss)
+            shard_check = bool(rep_many["n_devices"] == world and np.array_equal(one, many, equal_nan=True))
             call = al.complete_analysis if op == "complete_analysis" else al.consistency
             k_steps = max(2, min(a.steps, 5))
             times = []
@@ -484,6 +493,8 @@ def main():
                 "value": total_points * len(times) / sum(times), "unit": "points/s",
                 "ms_per_step": 1e3 * sum(times) / len(times), "steps": len(times),
                 "n_devices": world, "d2h_bytes_per_step": int(total_points * per * 8),
+                "bit_identical_to_one_device": shard_check,
+                "numa_nodes": [int(_native.lib().inflx_device_numa_node(d)) for d in range(world)],
                 "api": "GeneralisedAL." + call.__name__ + "(args, x0_start, x0_stop, x1_start, "
                 "x1_stop, N_x0, N_x1) in one process, lib.set_devices(range(N)): one host thread "
                 "per device, row shards written by DMA into the one pinned numpy output",

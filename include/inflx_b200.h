@@ -201,6 +201,12 @@ inflx_status inflx_points_eval(inflx_lib *lib, int op, const double *p, const do
  * registered with the driver (2-3x faster than cuMemHostAlloc, which remains the fall-back). */
 inflx_status inflx_host_alloc(size_t bytes, void **ptr);
 inflx_status inflx_host_free(void *ptr);
+/* The same for a block that `n_devices` devices will fill with equal row shards: slice d of the
+ * block is first-touched on the NUMA node device `devices[d]` is attached to, so every GPU's DMA
+ * writes stay on its own socket (inflx_host_alloc = this with the process's default devices;
+ * INFLATOX_NUMA=0 disables the placement). */
+inflx_status inflx_host_alloc_on(size_t bytes, const int *devices, int n_devices, void **ptr);
+int inflx_device_numa_node(int device);  /* -1: unknown */
 
 /* ---- measurement support: sustained FP64 FMA rate (2 flop per DFMA) of one device, from a
  * register-resident DFMA micro-kernel; the roofline denominator MEASURED_PEAKS.json lacks. */

@@ -143,6 +143,9 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.inflx_points_eval.argtypes = [vp, ci, dp, dp, c.c_uint64, c.c_double, dp]
     lib.inflx_measure_fp64_peak.argtypes = [ci, ci, dp, dp]
     lib.inflx_host_alloc.argtypes = [sz, c.POINTER(vp)]
+    lib.inflx_host_alloc_on.argtypes = [sz, c.POINTER(ci), ci, c.POINTER(vp)]
+    lib.inflx_device_numa_node.argtypes = [ci]
+    lib.inflx_device_numa_node.restype = ci
     lib.inflx_host_free.argtypes = [vp]
 
 

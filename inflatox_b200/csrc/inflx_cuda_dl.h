@@ -12,6 +12,7 @@
 
 #include <mutex>
 #include <string>
+#include <vector>
 
 #define INFLX_STR(x) #x
 #define INFLX_XSTR(x) INFLX_STR(x)
@@ -26,7 +27,7 @@
   X(cuEventRecord) X(cuEventSynchronize) X(cuEventElapsedTime) X(cuEventDestroy)                \
   X(cuLaunchKernel) X(cuGetErrorString) X(cuGetErrorName) X(cuPointerGetAttribute)              \
   X(cuMemGetInfo) X(cuMemHostRegister) X(cuMemHostUnregister) X(cuMemHostGetDevicePointer)    \
-  X(cuCtxGetCurrent)
+  X(cuCtxGetCurrent) X(cuDeviceGetPCIBusId)
 
 #define INFLX_NVRTC_FUNCS(X)                                                                    \
   X(nvrtcCreateProgram) X(nvrtcDestroyProgram) X(nvrtcCompileProgram) X(nvrtcGetProgramLogSize) \
@@ -97,11 +98,21 @@ struct Nvrtc {
 
  private:
   void load() {
-    const char* names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12",
-                           "/usr/local/cuda/lib64/libnvrtc.so", "libnvrtc.so.13"};
+    // The CUDA toolkit's NVRTC first, BY PATH: a bare soname resolves to whatever libnvrtc.so.12 is
+    // already mapped into the process, and `import torch` maps its own bundled (older) one - the
+    // cubin cache would then be keyed, and the kernels compiled, by a different compiler depending
+    // on import order (seen on the GPU box: bench.py imports torch, the tests do not).
+    std::vector<std::string> names;
+    if (const char* home = getenv("CUDA_HOME")) {
+      names.push_back(std::string(home) + "/lib64/libnvrtc.so.12");
+      names.push_back(std::string(home) + "/lib64/libnvrtc.so");
+    }
+    for (const char* n : {"/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so",
+                          "libnvrtc.so.12", "libnvrtc.so", "libnvrtc.so.13"})
+      names.push_back(n);
     std::string errs;
-    for (const char* n : names) {
-      handle = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+    for (const std::string& n : names) {
+      handle = dlopen(n.c_str(), RTLD_NOW | RTLD_LOCAL);
       if (handle) break;
       errs += std::string(dlerror()) + "; ";
     }

@@ -23,6 +23,8 @@
 #include <thread>
 #include <vector>
 
+#include <pthread.h>
+#include <sched.h>
 #include <sys/mman.h>
 
 #if defined(__x86_64__)
@@ -1372,13 +1374,60 @@ inflx_status inflx_measure_fp64_peak(int device, int repeats, double* tflops_bes
 // the driver.  Measured on the round-1 box for 12 GiB (tools/pin_probe.py): cuMemHostAlloc 5.7 s
 // (and it holds the driver's lock for all of it, stalling every concurrent launch/copy);
 // populate 1.3-1.4 s (no driver involvement) + cuMemHostRegister 1.0-2.3 s; same 55 GB/s D2H rate.
-inflx_status inflx_host_alloc(size_t bytes, void** ptr) {
+// NUMA placement.  The D2H copies are DMA writes into this memory; on a two-socket box a GPU whose
+// destination pages live on the other socket pushes its whole output over the inter-socket link
+// (round 1, 8 GPUs: 92 GB/s aggregate with everything on one node).  A block is therefore cut into
+// one slice per device - the same equal split the row sharding uses - and each slice is
+// first-touched by threads pinned to the CPUs of the NUMA node its GPU hangs off
+// (/sys/bus/pci/devices/<bus id>/numa_node).  INFLATOX_NUMA=0 turns the placement off.
+static int device_numa_node(CudaDriver& cu, int ordinal) {
+  CUdevice dev;
+  if (cu.p_cuDeviceGet(&dev, ordinal) != CUDA_SUCCESS) return -1;
+  char bus[64] = {0};
+  if (cu.p_cuDeviceGetPCIBusId(bus, sizeof bus, dev) != CUDA_SUCCESS) return -1;
+  for (char* c = bus; *c; ++c) *c = (char)tolower(*c);
+  FILE* f = fopen((std::string("/sys/bus/pci/devices/") + bus + "/numa_node").c_str(), "r");
+  if (!f) return -1;
+  int node = -1;
+  if (fscanf(f, "%d", &node) != 1) node = -1;
+  fclose(f);
+  return node;
+}
+static bool node_cpu_set(int node, cpu_set_t* set) {
+  CPU_ZERO(set);
+  if (node < 0) return false;
+  FILE* f = fopen(fmt("/sys/devices/system/node/node%d/cpulist", node).c_str(), "r");
+  if (!f) return false;
+  char buf[4096] = {0};
+  const bool ok = fgets(buf, sizeof buf, f) != nullptr;
+  fclose(f);
+  if (!ok) return false;
+  int n = 0;
+  for (char* tok = strtok(buf, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+    int a = 0, b = 0;
+    const int got = sscanf(tok, "%d-%d", &a, &b);
+    if (got == 1) b = a;
+    if (got >= 1)
+      for (int c = a; c <= b && c < CPU_SETSIZE; ++c) {
+        CPU_SET(c, set);
+        ++n;
+      }
+  }
+  return n > 0;
+}
+
+inflx_status inflx_host_alloc_on(size_t bytes, const int* devices, int n_devices, void** ptr) {
   *ptr = nullptr;
   CudaDriver& cu = CudaDriver::get();
   if (!cu.ok) return fail(INFLX_ERR_CUDA, cu.error);
+  std::vector<int> devs;
+  if (devices && n_devices > 0)
+    devs.assign(devices, devices + n_devices);
+  else
+    devs = default_devices();
+  if (devs.empty()) devs.push_back(0);
   DeviceState* dev = nullptr;  // a context must be current for cuMemHostAlloc / cuMemHostRegister
-  std::vector<int> d = default_devices();
-  inflx_status st = get_device(d.empty() ? 0 : d[0], &dev);
+  inflx_status st = get_device(devs[0], &dev);
   if (st) return st;
   CU_TRY(cu.p_cuCtxSetCurrent(dev->ctx));
   const char* mode = getenv("INFLATOX_HOST_ALLOC");
@@ -1390,24 +1439,39 @@ inflx_status inflx_host_alloc(size_t bytes, void** ptr) {
       const bool dbg = getenv("INFLATOX_DEBUG_POOL") != nullptr;
       const auto t0 = std::chrono::steady_clock::now();
       madvise(m, len, MADV_HUGEPAGE);
-      const unsigned nt = std::max(1u, std::min(4u, std::thread::hardware_concurrency()));
-      const size_t per = ((len / nt) + huge - 1) & ~(huge - 1);
+      const char* numa_env = getenv("INFLATOX_NUMA");
+      const bool numa = !(numa_env && !strcmp(numa_env, "0"));
+      const size_t nd = devs.size();
+      const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+      const unsigned per_slice = std::max<unsigned>(1, std::min(4u, hw) / (unsigned)nd);
       std::vector<std::thread> th;
-      for (unsigned k = 0; k < nt; ++k) {
-        const size_t lo = std::min(len, k * per), hi = std::min(len, lo + per);
-        if (lo < hi)
-          th.emplace_back([=] {
-            char* q = static_cast<char*>(m);
-            if (madvise(q + lo, hi - lo, 23 /* MADV_POPULATE_WRITE */) != 0)
-              for (size_t o = lo; o < hi; o += 4096) q[o] = 0;
-          });
+      std::string placed;
+      for (size_t d = 0; d < nd; ++d) {
+        // slice d = the bytes device d's row shard lands in (equal split, 2 MiB granularity)
+        const size_t s_lo = (len / huge * d / nd) * huge, s_hi = (len / huge * (d + 1) / nd) * huge;
+        const int node = numa ? device_numa_node(cu, devs[d]) : -1;
+        if (dbg) placed += fmt(" dev%d->node%d", devs[d], node);
+        const size_t per = (((s_hi - s_lo) / per_slice) + huge - 1) & ~(huge - 1);
+        for (unsigned k = 0; k < per_slice; ++k) {
+          const size_t lo = std::min(s_hi, s_lo + k * per), hi = std::min(s_hi, lo + per);
+          if (lo < hi)
+            th.emplace_back([=] {
+              cpu_set_t set;
+              if (node_cpu_set(node, &set))  // best effort: a cpuset that excludes the node stays put
+                pthread_setaffinity_np(pthread_self(), sizeof set, &set);
+              char* q = static_cast<char*>(m);
+              if (madvise(q + lo, hi - lo, 23 /* MADV_POPULATE_WRITE */) != 0)
+                for (size_t o = lo; o < hi; o += 4096) q[o] = 0;
+            });
+        }
       }
       for (auto& t : th) t.join();
       const auto t1 = std::chrono::steady_clock::now();
       const CUresult reg = cu.p_cuMemHostRegister(m, len, CU_MEMHOSTREGISTER_PORTABLE);
       if (dbg)
-        fprintf(stderr, "[inflx_host_alloc] %zu MiB: populate %.0f ms, register %.0f ms (rc %d)\n",
-                len >> 20, std::chrono::duration<double, std::milli>(t1 - t0).count(),
+        fprintf(stderr, "[inflx_host_alloc] %zu MiB:%s populate %.0f ms, register %.0f ms (rc %d)\n",
+                len >> 20, placed.c_str(),
+                std::chrono::duration<double, std::milli>(t1 - t0).count(),
                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1)
                     .count(),
                 (int)reg);
@@ -1422,6 +1486,14 @@ inflx_status inflx_host_alloc(size_t bytes, void** ptr) {
   }
   CU_TRY(cu.p_cuMemHostAlloc(ptr, bytes ? bytes : 1, CU_MEMHOSTALLOC_PORTABLE));
   return INFLX_OK;
+}
+inflx_status inflx_host_alloc(size_t bytes, void** ptr) {
+  return inflx_host_alloc_on(bytes, nullptr, 0, ptr);
+}
+// NUMA node a device's PCIe link is attached to, -1 when the platform does not say.
+int inflx_device_numa_node(int device) {
+  CudaDriver& cu = CudaDriver::get();
+  return cu.ok ? device_numa_node(cu, device) : -1;
 }
 inflx_status inflx_host_free(void* ptr) {
   if (!ptr) return INFLX_OK;

@@ -150,6 +150,7 @@ class InflatoxPyDyLib:
     def set_devices(self, ordinals) -> None:
         arr = (ctypes.c_int * len(ordinals))(*ordinals)
         _native.raise_for_status(_native.lib().inflx_set_devices(self._h, arr, len(ordinals)))
+        set_output_placement(self.devices())  # pinned outputs: one NUMA-local slice per device
 
     def devices(self) -> list[int]:
         buf = (ctypes.c_int * 64)()
@@ -350,10 +351,13 @@ class _PinnedBlock:
 
     total = 0  # bytes currently page-locked through this pool
 
-    def __init__(self, nbytes: int):
+    def __init__(self, nbytes: int, placement: tuple = ()):
         ptr = ctypes.c_void_p()
-        _native.raise_for_status(_native.lib().inflx_host_alloc(nbytes, ctypes.byref(ptr)))
-        self.ptr, self.nbytes = ptr, nbytes
+        devs = (ctypes.c_int * max(1, len(placement)))(*placement)
+        _native.raise_for_status(
+            _native.lib().inflx_host_alloc_on(nbytes, devs, len(placement), ctypes.byref(ptr))
+        )
+        self.ptr, self.nbytes, self.key = ptr, nbytes, (nbytes, tuple(placement))
         _PinnedBlock.total += nbytes
 
     def address(self) -> int:
@@ -379,7 +383,7 @@ class _PageableBlock:
 
     def __init__(self, nbytes: int):
         self.buf = np.empty(nbytes + 64, dtype=np.uint8)
-        self.nbytes = nbytes
+        self.nbytes, self.key = nbytes, nbytes
 
     def address(self) -> int:
         return (self.buf.ctypes.data + 63) & ~63
@@ -388,10 +392,19 @@ class _PageableBlock:
 # re-entrant: a lease's __del__ (below) takes it too, and the cyclic GC may run that finaliser on
 # the very thread that is inside one of the locked regions
 _pool_lock = threading.RLock()
-_pin_pool: dict[int, list[_PinnedBlock]] = {}
+_pin_pool: dict[tuple, list[_PinnedBlock]] = {}  # (bytes, placement) -> free blocks
 _page_pool: dict[int, list[_PageableBlock]] = {}
-_pin_jobs: dict[int, threading.Thread] = {}
+_pin_jobs: dict[tuple, threading.Thread] = {}
 _POOL_DEPTH = 4
+# devices whose row shards the next pinned outputs will receive (NUMA placement of the block's
+# slices, inflx_host_alloc_on); () = the engine's default devices.  Follows the last
+# open_inflx_dylib / InflatoxPyDyLib.set_devices call.
+_placement: tuple = ()
+
+
+def set_output_placement(devices) -> None:
+    global _placement
+    _placement = tuple(int(d) for d in devices)
 
 
 class _Lease:
@@ -404,7 +417,7 @@ class _Lease:
         try:
             pools = _pin_pool if self.block.pinned else _page_pool
             with _pool_lock:
-                pool = pools.setdefault(self.block.nbytes, [])
+                pool = pools.setdefault(self.block.key, [])
                 if len(pool) < _POOL_DEPTH:
                     pool.append(self.block)
         except Exception:  # interpreter shutdown: module globals may already be gone
@@ -442,11 +455,12 @@ def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
     blocks for seconds on a multi-GB array) and pooled.  Outputs allocated here are written by DMA
     straight from the GPU(s)."""
     shape, count, nbytes = _round_block(shape, dtype)
+    key = (nbytes, _placement)
     with _pool_lock:
-        pool = _pin_pool.get(nbytes)
+        pool = _pin_pool.get(key)
         block = pool.pop() if pool else None
     if block is None:
-        block = _PinnedBlock(nbytes)
+        block = _PinnedBlock(nbytes, _placement)
     return _as_array(block, shape, count, dtype)
 
 
@@ -467,11 +481,12 @@ def host_output(shape, dtype=np.float64) -> np.ndarray:
     if mode == "sync":
         return pinned_empty(shape, dtype)
     shape, count, nbytes = _round_block(shape, dtype)
+    key = (nbytes, _placement)
     with _pool_lock:
-        pool = _pin_pool.get(nbytes)
+        pool = _pin_pool.get(key)
         block = pool.pop() if pool else None
         if block is None:
-            job = _pin_jobs.get(nbytes)
+            job = _pin_jobs.get(key)
             if (
                 mode != "off"
                 and (job is None or not job.is_alive())
@@ -479,24 +494,24 @@ def host_output(shape, dtype=np.float64) -> np.ndarray:
             ):
                 seen = _gate.completed
 
-                def pin(nb=nbytes):
+                def pin(nb=nbytes, key=key):
                     if mode != "eager":
                         _gate.wait_idle_after(seen, timeout=10.0)
                     if _gate.closing:
                         return
                     _pool_debug(f"pinning {nb >> 20} MiB")
                     try:
-                        blk = _PinnedBlock(nb)
+                        blk = _PinnedBlock(nb, key[1])
                     except Exception:
                         return  # no GPU / out of lockable memory: stay on the staged path
                     _pool_debug(f"pinned {nb >> 20} MiB")
                     with _pool_lock:
-                        _pin_pool.setdefault(nb, []).append(blk)
+                        _pin_pool.setdefault(key, []).append(blk)
 
                 # not a daemon: interpreter shutdown waits for a page-lock in flight instead of
                 # tearing the driver down under it
                 job = threading.Thread(target=pin, daemon=False)
-                _pin_jobs[nbytes] = job
+                _pin_jobs[key] = job
                 job.start()
             pages = _page_pool.get(nbytes)
             block = pages.pop() if pages else None

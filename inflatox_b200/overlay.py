@@ -5,8 +5,9 @@ and of the reference's own tests - run on the GPU path without a single edit in 
 
     python -m inflatox_b200.overlay /path/to/reference/checkout /path/to/site-dir
 
-Layout written under the destination (a directory to put on PYTHONPATH; git-ignored here as
-baseline/_ref, built by `__graft_entry__.build()` when the reference checkout is present):
+Layout written under the destination (put `<dest>` first and `<dest>/_stubs` last on PYTHONPATH;
+git-ignored here as baseline/_ref, built by `__graft_entry__.build()` when the reference checkout is
+present):
 
     inflatox/__init__.py, symbolic.py, version.py, background.py   copied verbatim from the reference
                                                                    (python/inflatox/; symbolic model
@@ -18,9 +19,13 @@ baseline/_ref, built by `__graft_entry__.build()` when the reference checkout is
                                                                    reference's module names
     inflatox-<version>.dist-info/METADATA                          so that version.py's
                                                                    importlib.metadata lookup resolves
-    interruptingcow.py                                             the reference's only dependency
-                                                                   missing from this image: a SIGALRM
-                                                                   `timeout` context manager
+    _stubs/interruptingcow.py, _stubs/IPython/display.py           stand-ins for the two third-party
+                                                                   packages the reference imports that
+                                                                   this image lacks (a SIGALRM `timeout`
+                                                                   context manager; `display`, which
+                                                                   symbolic.py:281 calls when a builder
+                                                                   is not silent).  Put `_stubs` LAST on
+                                                                   PYTHONPATH: a real installation wins
     reference_tests/                                               the reference's tests/ directory,
                                                                    verbatim (acceptance tests)
     MANIFEST.json                                                  sha256 of every copied file
@@ -91,6 +96,23 @@ def timeout(seconds, exception=RuntimeError):
 '''
 
 
+IPYTHON_DISPLAY = '''"""Minimal stand-in for IPython.display (IPython is absent from this image): the reference's
+non-silent model builder shows its intermediate expressions with `display`
+(reference python/inflatox/symbolic.py:274-284); here they are pretty-printed to stdout."""
+
+
+def display(*objs, **kwargs):
+    try:
+        import sympy
+
+        for o in objs:
+            print(sympy.pretty(o))
+    except Exception:
+        for o in objs:
+            print(o)
+'''
+
+
 def _sha(path: str) -> str:
     with open(path, "rb") as fh:
         return hashlib.sha256(fh.read()).hexdigest()
@@ -122,8 +144,17 @@ def assemble(reference_root: str, dest: str) -> dict:
     for name, text in SHIMS.items():
         with open(os.path.join(pkg, name), "w") as fh:
             fh.write(text)
-    with open(os.path.join(dest, "interruptingcow.py"), "w") as fh:
+    stubs = os.path.join(dest, "_stubs")
+    shutil.rmtree(stubs, ignore_errors=True)
+    os.makedirs(os.path.join(stubs, "IPython"))
+    with open(os.path.join(stubs, "interruptingcow.py"), "w") as fh:
         fh.write(INTERRUPTINGCOW)
+    with open(os.path.join(stubs, "IPython", "__init__.py"), "w") as fh:
+        fh.write('"""Stand-in package, see display.py."""\n')
+    with open(os.path.join(stubs, "IPython", "display.py"), "w") as fh:
+        fh.write(IPYTHON_DISPLAY)
+    if os.path.exists(os.path.join(dest, "interruptingcow.py")):
+        os.remove(os.path.join(dest, "interruptingcow.py"))
     info = os.path.join(dest, f"inflatox-{version}.dist-info")
     shutil.rmtree(info, ignore_errors=True)
     os.makedirs(info)

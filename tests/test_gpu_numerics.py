@@ -97,12 +97,13 @@ def test_speculative_sqrt_is_ieee_whenever_it_claims_so(mod):
     assert _same(q[ok], qe[ok]).all()
     m = (a > 1e-100) & (a < 1e100)
     assert (bad[m] == 0).all()
+    # the test is on |high word| read as a float: conservative beyond 2^1017 (nvcc: 2^1024)
     # zero, inf, -0 and NaN take the slow path (a NaN argument means a NaN upstream, whose quotients
     # have flagged the point anyway); a negative argument of ordinary magnitude is NaN on the fast
     # path too and must NOT be flagged (omega / eta are NaN by design on 10-60 % of a grid)
     assert bad[0] == 1 and bad[1] == 1 and bad[2] == 1 and bad[3] == 1
     assert bad[5] == 0 and np.isnan(q[[2, 5, 7]]).all()
-    neg = (a < -1e-290) & np.isfinite(a)
+    neg = (a < -1e-290) & (a > -1e300)
     assert neg.sum() > 1000 and (bad[neg] == 0).all() and np.isnan(q[neg]).all()
 
 

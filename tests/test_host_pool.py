@@ -43,11 +43,11 @@ def test_blocks_return_to_the_pool_and_are_reused():
     del a
     gc.collect()
     _wait_jobs()
-    pools = rs._pin_pool if rs._pin_pool.get(nbytes) else rs._page_pool
-    assert pools.get(nbytes), "the block was not returned"
+    pin_key = (nbytes, rs._placement)  # pinned blocks are pooled per (size, NUMA placement)
+    assert rs._pin_pool.get(pin_key) or rs._page_pool.get(nbytes), "the block was not returned"
     b = rs.host_output((1 << 20,))
     # without a GPU the pageable block comes back; with one, the freshly pinned block may be used
-    assert b.ctypes.data == addr or rs._pin_pool.get(nbytes) is not None
+    assert b.ctypes.data == addr or rs._pin_pool.get(pin_key) is not None
     views = [rs.host_output((1 << 20,)) for _ in range(rs._POOL_DEPTH + 2)]
     del views, b
     gc.collect()
@@ -85,7 +85,7 @@ def test_pin_budget_env(monkeypatch):
 def test_deferred_pin_job_waits_for_an_engine_call(monkeypatch):
     monkeypatch.setenv("INFLATOX_PIN_MODE", "deferred")
     a = rs.host_output((1 << 19, 3))
-    job = rs._pin_jobs[rs._round_block((1 << 19, 3), np.float64)[2]]
+    job = rs._pin_jobs[(rs._round_block((1 << 19, 3), np.float64)[2], rs._placement)]
     time.sleep(0.2)
     assert job.is_alive(), "the job must wait until the call the array is for has returned"
     with rs._gate:  # stands in for the engine call

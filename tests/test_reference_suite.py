@@ -40,7 +40,10 @@ def _overlay() -> str:
 def _run_reference_test(name: str, timeout: int) -> None:
     site = _overlay()
     env = dict(os.environ)
-    env["PYTHONPATH"] = os.pathsep.join([site, cases.ROOT] + [p for p in [env.get("PYTHONPATH")] if p])
+    # overlay first, the stand-ins for absent third-party packages last (a real one wins)
+    env["PYTHONPATH"] = os.pathsep.join(
+        [site, cases.ROOT] + [p for p in [env.get("PYTHONPATH")] if p] + [os.path.join(site, "_stubs")]
+    )
     env.setdefault("INFLATOX_CACHE_DIR", os.path.join(cases.ROOT, "tests", ".cubin_cache"))
     r = subprocess.run(
         [sys.executable, "-m", "pytest", os.path.join(site, "reference_tests", name), "-q", "-x",

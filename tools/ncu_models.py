@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Per-model ncu table (profiles/ncu_models_r1.md) from one `ncu --set full` capture per config.
+"""Per-model ncu table (profiles/ncu_models_r<N>.md) from one `ncu --set full` capture per config.
 
     python tools/ncu_models.py C1=gpurun_out/prof_C1_r1k.ncu-rep C2=… --out profiles/ncu_models_r1.md
 """
@@ -22,12 +22,23 @@ ROWS = [
     ("issue slots busy %", "smsp__issue_active.avg.pct_of_peak_sustained_active"),
     ("DRAM written", "dram__bytes_write.sum"),
     ("DRAM read", "dram__bytes_read.sum"),
+    ("L2 write sectors (32 B)", "lts__t_sectors_op_write.sum"),
+    ("local-memory (spill) store sectors", "l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum"),
+    ("local-memory (spill) load sectors", "l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum"),
+    ("warp instructions executed", "smsp__inst_executed.sum"),
+    ("stall: wait / issue", "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio"),
+    ("stall: math pipe throttle / issue", "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio"),
+    ("stall: not selected / issue", "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio"),
+    ("stall: long scoreboard / issue", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio"),
 ]  # fmt: skip
 TITLES = {
     "C1": "C1: hyperinflation, complete_analysis, 1000^2",
     "C2": "C2: angular, consistency_only, 4096^2",
     "C3": "C3: EGNO, complete_analysis, 16384^2",
     "C4": "C4: D5-brane, complete_analysis, 16384^2",
+    "C6": "C6: angular, complete_analysis, 16384^2",
+    "C7": "C7: hyperinflation, complete_analysis, 16384^2",
+    "C8": "C8: doc model, complete_analysis, 16384^2",
 }
 
 
@@ -43,7 +54,7 @@ def main():
         "# ncu per model - dominant kernel `inflx_grid_<op>`, 1 x B200",
         "",
         "One `ncu --set full --clock-control none --import-source on -k regex:inflx_grid -c 1 python "
-        "bench.py --config Cx --steps 2 --warmup 1 --no-cpu --no-e2e` per config, each after the "
+        "bench.py --config Cx --steps 2 --warmup 1 --no-cpu --no-e2e --no-all` per config, each after the "
         "same command had exited 0 without ncu (reports: "
         + ", ".join(p for _, p in reps)
         + "; binary, not committed).",
