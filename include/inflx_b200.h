@@ -191,6 +191,14 @@ typedef struct {
 inflx_status inflx_grid_eval(inflx_lib *lib, const inflx_grid_request *req,
                              inflx_grid_report *report /* may be NULL */);
 
+/* The static sharding rule (the reference has a single shared-memory pool,
+ * src/anguelova.rs:219-251): shard `index` of `count` owns rows [out[0], out[1]) and parameter
+ * vectors [out[2], out[3]).  A sweep with at least `count` vectors is cut into blocks of vectors,
+ * anything else into contiguous row blocks.  inflx_grid_eval applies it over a handle's devices,
+ * inflatox_b200.sharding over the ranks of a one-process-per-GPU job.  Needs no GPU. */
+inflx_status inflx_shard_of(uint64_t n_rows, uint64_t n_vectors, uint64_t index, uint64_t count,
+                            uint64_t out[4]);
+
 /* Point list evaluation behind the on-trajectory and scalar entry points. */
 inflx_status inflx_points_eval(inflx_lib *lib, int op, const double *p, const double *xs,
                                uint64_t n, double aux, double *out);

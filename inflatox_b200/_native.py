@@ -119,6 +119,7 @@ def _declare(lib: ctypes.CDLL) -> None:
         c.POINTER(vp),
     ]  # fmt: skip
     lib.inflx_nvrtc_version.argtypes = [c.POINTER(ci), c.POINTER(ci)]
+    lib.inflx_shard_of.argtypes = [c.c_uint64, c.c_uint64, c.c_uint64, c.c_uint64, c.POINTER(c.c_uint64)]
     lib.inflx_set_devices.argtypes = [vp, c.POINTER(ci), ci]
     lib.inflx_get_devices.argtypes = [vp, c.POINTER(ci), ci]
     lib.inflx_complete_analysis.argtypes = [vp, dp, sz, dp, sz, sz, sz, dp, sz, sz, ci, sz]

@@ -852,6 +852,26 @@ int inflx_get_devices(const inflx_lib* lib, int* ordinals, int capacity) {
   return n;
 }
 
+// ---- static sharding: the ONE implementation of the rule ------------------------
+inflx_status inflx_shard_of(uint64_t n_rows, uint64_t n_vectors, uint64_t index, uint64_t count,
+                            uint64_t out[4]) {
+  if (count == 0 || index >= count)
+    return fail(INFLX_ERR_SHAPE, fmt("shard %llu outside a partition into %llu",
+                                     (unsigned long long)index, (unsigned long long)count));
+  if (n_vectors >= count && count > 1 && n_vectors > 1) {  // a sweep: blocks of parameter vectors
+    out[0] = 0;
+    out[1] = n_rows;
+    out[2] = n_vectors * index / count;
+    out[3] = n_vectors * (index + 1) / count;
+  } else {  // one grid (or fewer vectors than shards): contiguous row blocks
+    out[0] = n_rows * index / count;
+    out[1] = n_rows * (index + 1) / count;
+    out[2] = 0;
+    out[3] = n_vectors;
+  }
+  return INFLX_OK;
+}
+
 // ---- generic grid evaluation -----------------------------------------------------------------
 inflx_status inflx_grid_eval(inflx_lib* lib, const inflx_grid_request* rq,
                              inflx_grid_report* report) {
@@ -874,19 +894,15 @@ inflx_status inflx_grid_eval(inflx_lib* lib, const inflx_grid_request* rq,
   if (rq->out_is_device && devs.size() != 1) devs.resize(1);
   if (devs.empty()) return fail(INFLX_ERR_CUDA, "no CUDA device selected");
 
-  // shards: parameter vectors block-distributed when there are enough, else row blocks
+  // shards: parameter vectors block-distributed when there are enough, else row blocks - the one
+  // rule (inflx_shard_of) that inflatox_b200.sharding applies across the ranks of a torchrun job
   std::vector<Shard> shards;
   const uint64_t nd = devs.size(), S = rq->n_vectors, R = rq->row_end - rq->row_begin;
-  if (S >= nd && nd > 1) {
-    for (uint64_t d = 0; d < nd; ++d) {
-      uint64_t a = S * d / nd, b = S * (d + 1) / nd;
-      if (b > a) shards.push_back({rq->row_begin, rq->row_end, a, b, devs[d]});
-    }
-  } else {
-    for (uint64_t d = 0; d < nd; ++d) {
-      uint64_t a = rq->row_begin + R * d / nd, b = rq->row_begin + R * (d + 1) / nd;
-      if (b > a) shards.push_back({a, b, 0, S, devs[d]});
-    }
+  for (uint64_t d = 0; d < nd; ++d) {
+    uint64_t o[4];
+    inflx_shard_of(R, S, d, nd, o);
+    if (o[1] > o[0] && o[3] > o[2])
+      shards.push_back({rq->row_begin + o[0], rq->row_begin + o[1], o[2], o[3], devs[d]});
   }
   std::vector<ShardResult> results(shards.size());
   auto work = [&](size_t i) {
