@@ -155,7 +155,7 @@ struct DeviceState {
   CUevent ev_t0 = nullptr, ev_t1 = nullptr, ev_g0 = nullptr, ev_g1 = nullptr;
   std::mutex mu;  // one grid call at a time per device (scratch buffers are shared)
   DevBuf d_p, d_pc, d_rc, d_cc, d_xs, d_out[2];
-  PinBuf stage[2];
+  PinBuf stage[2], stage_in[2];
   // A call that ran on a CALLER's stream returns without synchronising; its kernels may still be
   // reading the shared scratch (d_p, d_pc, d_rc, d_cc) and the module's __constant__ bank.
   // ev_user marks its end: the next user of the scratch waits for it on its own stream.
@@ -995,15 +995,56 @@ inflx_status inflx_points_eval(inflx_lib* lib, int opi, const double* p, const d
     if ((st = launch(cu, gm->params, 1, 1, 1, 64, cs, args))) return st;
     CU_TRY(cu.p_cuMemcpyDtoDAsync(gm->pc_sym, dev->d_pc.ptr, NPF * 8, cs));
   }
-  const uint64_t chunk = 1ull << 22, opb = op.out_bytes;
-  if ((st = ensure_dev(cu, dev->d_xs, std::min(n, chunk) * 16))) return st;
-  if ((st = ensure_dev(cu, dev->d_out[0], std::min(n, chunk) * opb))) return st;
-  for (uint64_t b = 0; b < n; b += chunk) {
-    uint64_t m = std::min(chunk, n - b);
-    CU_TRY(cu.p_cuMemcpyHtoDAsync(dev->d_xs.ptr, xs + 2 * b, m * 16, cs));
-    void* args[] = {&dev->d_out[0].ptr, &dev->d_xs.ptr, &m, &aux};
-    if ((st = launch(cu, fn, (unsigned)((m + 127) / 128), 1, 1, 128, cs, args))) return st;
-    CU_TRY(cu.p_cuMemcpyDtoHAsync((char*)out + b * opb, dev->d_out[0].ptr, m * opb, cs));
+  const uint64_t opb = op.out_bytes;
+  if (n <= (1ull << 16)) {  // a trajectory of the reference tests' size: one launch, plain copies
+    if ((st = ensure_dev(cu, dev->d_xs, n * 16))) return st;
+    if ((st = ensure_dev(cu, dev->d_out[0], n * opb))) return st;
+    CU_TRY(cu.p_cuMemcpyHtoDAsync(dev->d_xs.ptr, xs, n * 16, cs));
+    void* args[] = {&dev->d_out[0].ptr, &dev->d_xs.ptr, &n, &aux};
+    if ((st = launch(cu, fn, (unsigned)((n + 127) / 128), 1, 1, 128, cs, args))) return st;
+    CU_TRY(cu.p_cuMemcpyDtoHAsync(out, dev->d_out[0].ptr, n * opb, cs));
+    CU_TRY(cu.p_cuStreamSynchronize(cs));
+  } else {
+    // long point lists: 1 Mi-point chunks through page-locked staging, two slots - the upload and
+    // kernel of chunk k+1 run while chunk k's result travels back on the copy stream and chunk
+    // k-1's is unstaged into the caller's (pageable) array
+    const uint64_t chunk = 1ull << 20;
+    if ((st = ensure_dev(cu, dev->d_xs, chunk * 16))) return st;
+    for (int i = 0; i < 2; ++i) {
+      if ((st = ensure_dev(cu, dev->d_out[i], chunk * opb))) return st;
+      if ((st = ensure_pin(cu, dev->stage[i], chunk * opb))) return st;
+      if ((st = ensure_pin(cu, dev->stage_in[i], chunk * 16))) return st;
+    }
+    struct {
+      bool active = false;
+      uint64_t b = 0, m = 0;
+    } pend[2];
+    auto drain = [&](int slot) -> inflx_status {
+      if (!pend[slot].active) return INFLX_OK;
+      CU_TRY(cu.p_cuEventSynchronize(dev->ev_copied[slot]));
+      parallel_memcpy((char*)out + pend[slot].b * opb, dev->stage[slot].ptr, pend[slot].m * opb);
+      pend[slot].active = false;
+      return INFLX_OK;
+    };
+    uint64_t k = 0;
+    for (uint64_t b = 0; b < n; b += chunk, ++k) {
+      const int slot = (int)(k & 1);
+      uint64_t m = std::min(chunk, n - b);
+      if ((st = drain(slot))) return st;  // also: stage_in[slot] is free again (its kernel ran)
+      parallel_memcpy(dev->stage_in[slot].ptr, xs + 2 * b, m * 16);
+      CU_TRY(cu.p_cuMemcpyHtoDAsync(dev->d_xs.ptr, dev->stage_in[slot].ptr, m * 16, cs));
+      void* args[] = {&dev->d_out[slot].ptr, &dev->d_xs.ptr, &m, &aux};
+      if ((st = launch(cu, fn, (unsigned)((m + 127) / 128), 1, 1, 128, cs, args))) return st;
+      CU_TRY(cu.p_cuEventRecord(dev->ev_done[slot], cs));
+      CU_TRY(cu.p_cuStreamWaitEvent(dev->copy, dev->ev_done[slot], 0));
+      CU_TRY(cu.p_cuMemcpyDtoHAsync(dev->stage[slot].ptr, dev->d_out[slot].ptr, m * opb, dev->copy));
+      CU_TRY(cu.p_cuEventRecord(dev->ev_copied[slot], dev->copy));
+      pend[slot].active = true;
+      pend[slot].b = b;
+      pend[slot].m = m;
+    }
+    if ((st = drain((int)(k & 1)))) return st;
+    if ((st = drain((int)((k & 1) ^ 1)))) return st;
     CU_TRY(cu.p_cuStreamSynchronize(cs));
   }
   dev->user_pending = false;

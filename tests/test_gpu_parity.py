@@ -191,6 +191,63 @@ def test_on_trajectory(model):
         check(model, o1, getattr(orc, fn + "_on_trajectory")(p, xs), what=fn)
 
 
+def test_long_point_list_equals_short_batches():
+    """2.3 M points (the chunked, double-buffered path of inflx_points_eval) against the same points
+    sent in batches of 50 000 (one launch, plain copies): not a bit may differ, ragged tail included."""
+    lib = rs.open_inflx_dylib(cases.artifact("angular").shared_object_path, False)
+    lib.set_devices([0])
+    p, ext = cases.params("angular"), cases.EXTENT["angular"]
+    rng = np.random.default_rng(11)
+    n = 2_300_017
+    xs = np.ascontiguousarray(
+        np.stack([rng.uniform(ext[0], ext[1], n), rng.uniform(ext[2], ext[3], n)], axis=1)
+    )
+    long = np.zeros((n, 6))
+    rs.complete_analysis_on_trajectory(lib, p, xs, long, False, 1)
+    for b in range(0, n, 500_000):  # spot-check five batches incl. the chunk boundaries
+        for lo in (b, max(0, b + (1 << 20) - 25_000) if b + (1 << 20) < n else b):
+            hi = min(n, lo + 50_000)
+            short = np.zeros((hi - lo, 6))
+            rs.complete_analysis_on_trajectory(lib, p, np.ascontiguousarray(xs[lo:hi]), short, False, 1)
+            assert np.array_equal(long[lo:hi], short, equal_nan=True), (lo, hi)
+    tail = np.zeros((17, 6))
+    rs.complete_analysis_on_trajectory(lib, p, np.ascontiguousarray(xs[-17:]), tail, False, 1)
+    assert np.array_equal(long[-17:], tail, equal_nan=True)
+    one = np.zeros(n)
+    rs.epsilon_v_only_on_trajectory(lib, p, xs, one, False, 1)
+    ref = oracle.Oracle("angular").epsilon_v_only_on_trajectory(p, xs[:100_000])
+    check("angular", one[:100_000], ref, what="long trajectory eps_V")
+
+
+def test_two_streams_on_one_device_do_not_corrupt_each_other():
+    """ADVICE (round 1): a device-resident call on a CALLER's stream returns without synchronising
+    while its kernels still read the device's shared scratch and the module's __constant__ bank.
+    Interleave calls with DIFFERENT parameter vectors on two streams and on the internal stream:
+    every output must equal the one a synchronous call produces."""
+    import torch
+
+    lib = rs.open_inflx_dylib(cases.artifact("egno").shared_object_path, False)
+    lib.set_devices([0])
+    p0, ext = cases.params("egno"), cases.EXTENT["egno"]
+    n0, n1 = 1536, 1024
+    ps = [p0, p0 * np.array([1.5, 1.0, 1.0, 1.0]), p0 * np.array([1.0, 1.1, 1.0, 1.0])]
+    want = []
+    for p in ps:
+        h = np.zeros((n0, n1, 6))
+        rs.grid_eval(lib, "complete_analysis", p, h, n0, n1, ext)
+        want.append(h)
+    s1, s2 = torch.cuda.Stream(device=0), torch.cuda.Stream(device=0)
+    outs = [torch.empty(n0 * n1 * 6, dtype=torch.float64, device="cuda:0") for _ in range(6)]
+    order = [(0, s1), (1, s2), (2, s1), (0, s2), (1, None), (2, s2)]
+    for (k, st), d in zip(order, outs):
+        rs.grid_eval(lib, "complete_analysis", ps[k], None, n0, n1, ext, device=0,
+                     out_device_ptr=d.data_ptr(), stream=None if st is None else st.cuda_stream)  # fmt: skip
+    torch.cuda.synchronize()
+    for (k, _), d in zip(order, outs):
+        assert np.array_equal(d.cpu().numpy().reshape(n0, n1, 6), want[k], equal_nan=True), k
+    del lib  # inflx_close after asynchronous work: must wait for it, not unload under it
+
+
 def test_edge_shapes():
     lib = rs.open_inflx_dylib(cases.artifact("doc").shared_object_path, False)
     lib.set_devices([0])
