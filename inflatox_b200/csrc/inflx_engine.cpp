@@ -311,7 +311,7 @@ using namespace inflx;
 struct GroupModule {
   CUmodule mod = nullptr;
   CUdeviceptr pc_sym = 0;
-  CUfunction params = nullptr, rows = nullptr, cols = nullptr;
+  CUfunction params = nullptr, rows = nullptr, cols = nullptr, prologue = nullptr;
   std::map<std::string, CUfunction> fns;
 };
 
@@ -353,6 +353,8 @@ static inflx_status load_module(inflx_lib* lib, DeviceState* dev, const char* gr
   CU_TRY(cu.p_cuModuleGetFunction(&gm->params, gm->mod, "inflx_params"));
   CU_TRY(cu.p_cuModuleGetFunction(&gm->rows, gm->mod, "inflx_rows"));
   if (g->ncf) CU_TRY(cu.p_cuModuleGetFunction(&gm->cols, gm->mod, "inflx_cols"));
+  if (cu.p_cuModuleGetFunction(&gm->prologue, gm->mod, "inflx_prologue") != CUDA_SUCCESS)
+    gm->prologue = nullptr;  // artefact of an older generator: the three-step prologue is used
   *out = gm.get();
   lib->modules[key] = std::move(gm);
   return INFLX_OK;
@@ -453,18 +455,27 @@ static inflx_status run_shard(inflx_lib* lib, const inflx_grid_request& rq, cons
   CUstream cs = (to_device && rq.stream) ? (CUstream)rq.stream : dev->compute;
   if ((st = order_after_user_stream(cu, dev, cs))) return st;
 
-  // (1) parameters -> P-frontier values of every vector of the shard
-  if (P > 0) {
-    if ((st = ensure_dev(cu, dev->d_p, S * P * 8))) return st;
-    CU_TRY(cu.p_cuMemcpyHtoDAsync(dev->d_p.ptr, rq.params + sh.sb * P, S * P * 8, cs));
-    res.h2d += S * P * 8;
-  }
-  if (NPF > 0) {
-    if ((st = ensure_dev(cu, dev->d_pc, S * NPF * 8))) return st;
-    uint32_t nv = (uint32_t)S;
-    void* args[] = {&dev->d_p.ptr, &dev->d_pc.ptr, &nv};
-    if ((st = launch(cu, gm->params, (unsigned)((S + 63) / 64), 1, 1, 64, cs, args))) return st;
-    res.launches++;
+  // (1) parameters -> P-frontier values of every vector of the shard.  One vector: the fused
+  // prologue kernel of the first row chunk does it (parameters by value in its argument buffer,
+  // no H2D copy, no separate inflx_params / inflx_rows launch); a sweep: H2D + inflx_params.
+  const bool fused = S == 1 && !sweep && gm->prologue != nullptr && getenv("INFLATOX_NO_FUSED_PROLOGUE") == nullptr;
+  std::vector<double> pv(std::max<uint32_t>(P, 1), 0.0);
+  if (P > 0) memcpy(pv.data(), rq.params + sh.sb * P, P * 8);
+  if (NPF > 0 && (st = ensure_dev(cu, dev->d_pc, S * NPF * 8))) return st;
+  if (!fused) {
+    if (P > 0) {
+      if ((st = ensure_dev(cu, dev->d_p, S * P * 8))) return st;
+      CU_TRY(cu.p_cuMemcpyHtoDAsync(dev->d_p.ptr, rq.params + sh.sb * P, S * P * 8, cs));
+      res.h2d += S * P * 8;
+    }
+    if (NPF > 0) {
+      uint32_t nv = (uint32_t)S;
+      void* args[] = {&dev->d_p.ptr, &dev->d_pc.ptr, &nv};
+      if ((st = launch(cu, gm->params, (unsigned)((S + 63) / 64), 1, 1, 64, cs, args))) return st;
+      res.launches++;
+    }
+  } else {
+    res.h2d += P * 8;  // the bytes travel in the launch's argument buffer
   }
 
   // (2) chunking: vectors first (bounded by the constant bank), then rows
@@ -579,15 +590,22 @@ static inflx_status run_shard(inflx_lib* lib, const inflx_grid_request& rq, cons
   uint64_t k = 0;
   for (uint64_t s0 = 0; s0 < S; s0 += s_chunk) {
     const uint64_t sc = std::min(s_chunk, S - s0);
-    if (NPF)
-      CU_TRY(cu.p_cuMemcpyDtoDAsync(gm->pc_sym, dev->d_pc.ptr + s0 * NPF * 8, sc * NPF * 8, cs));
-    if (NCF) {  // column pre-pass: the column block holds a correctly rounded libm call
-      uint32_t n1c = (uint32_t)n1;
-      void* args[] = {&dev->d_cc.ptr, &of1, &dx1, &n1c};
-      if ((st = launch(cu, gm->cols, (unsigned)((n1 + 127) / 128), (unsigned)sc, 1, 128, cs, args)))
-        return st;
-      res.launches++;
-    }
+    // P-frontier values -> the module's __constant__ bank, then the column pre-pass (which reads
+    // the bank); with the fused prologue both follow the first row chunk's prologue launch
+    auto bank_and_columns = [&]() -> inflx_status {
+      if (NPF)
+        CU_TRY(cu.p_cuMemcpyDtoDAsync(gm->pc_sym, dev->d_pc.ptr + s0 * NPF * 8, sc * NPF * 8, cs));
+      if (NCF) {  // column pre-pass: the column block holds an out-of-line libm call
+        uint32_t n1c = (uint32_t)n1;
+        void* args[] = {&dev->d_cc.ptr, &of1, &dx1, &n1c};
+        inflx_status s2 = launch(cu, gm->cols, (unsigned)((n1 + 127) / 128), (unsigned)sc, 1, 128, cs, args);
+        if (s2) return s2;
+        res.launches++;
+      }
+      return INFLX_OK;
+    };
+    if (!fused && (st = bank_and_columns())) return st;
+    bool first_chunk = true;
     for (uint64_t r0 = sh.rb; r0 < sh.re; r0 += rows_chunk, ++k) {
       const uint64_t rc = std::min(rows_chunk, sh.re - r0);
       const int slot = (int)(k & 1);
@@ -595,13 +613,21 @@ static inflx_status run_shard(inflx_lib* lib, const inflx_grid_request& rq, cons
         if ((st = finish(slot))) return st;  // buffer `slot` must be drained before reuse
       }
       uint32_t n_rows = (uint32_t)rc, n1u = (uint32_t)n1;
-      if (NRF) {
+      if (fused && first_chunk) {
+        uint64_t rbeg = r0;
+        void* args[] = {pv.data(), &dev->d_pc.ptr, &dev->d_rc.ptr, &of0, &dx0, &rbeg, &n_rows};
+        const unsigned blocks = (unsigned)std::max<uint64_t>(1, (rc + 127) / 128);
+        if ((st = launch(cu, gm->prologue, blocks, 1, 1, 128, cs, args))) return st;
+        res.launches++;
+        if ((st = bank_and_columns())) return st;
+      } else if (NRF) {
         uint64_t rbeg = r0;
         void* args[] = {&dev->d_rc.ptr, &of0, &dx0, &rbeg, &n_rows};
         if ((st = launch(cu, gm->rows, (unsigned)((rc + 127) / 128), (unsigned)sc, 1, 128, cs, args)))
           return st;
         res.launches++;
       }
+      first_chunk = false;
       CUdeviceptr outp;
       uint64_t comp_stride = sc * rc * n1;
       if (to_device) {

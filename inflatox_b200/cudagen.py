@@ -565,6 +565,45 @@ class GroupProgram:
             "  (void)pbase; (void)x0; (void)rr;\n" + body + stores + "}\n\n"
         )
 
+        # ---- (2a) fused prologue for ONE parameter vector: parameter block + row block in one launch.
+        # The parameters arrive BY VALUE in the kernel's argument buffer (no H2D copy), every thread
+        # evaluates the (cheap) parameter block itself and then its row; thread 0 also writes the
+        # P-frontier values out for the copy into the grid kernel's __constant__ bank.  Replaces
+        # H2D + inflx_params + inflx_rows on a call's first row chunk: 5 dependent operations in
+        # front of the grid kernel become 3 (the ~47 us serial prologue of round 1 is what a
+        # 1 ms step on 8 GPUs loses most).  Same operations -> same bits.
+        scope = self._leaf_scope({("p", k): f"pv.v[{k}]" for k in range(self.n_params)})
+        scope.update(self._leaf_scope({("x", 0): "x0"}))
+        body_p = self._block(self.nodes_of("P"), scope, "  ", spec=False)
+        for n in self.p_slot:
+            if n not in scope and self.node(n)[0] == "rcp":
+                body_p += f"  const double t{n} = {self._expr(n, scope, False)};\n"
+                scope[n] = f"t{n}"
+        stores_p = "".join(
+            f"    pc_out[{k}] = {self._ref(n, scope)};\n" for n, k in self.p_slot.items()
+        )
+        body_r = self._block(self.nodes_of("R", self.grid_nodes), scope, "  ", spec=False)
+        for n in self.r_slot:
+            if n not in scope and self.node(n)[0] == "rcp":
+                body_r += f"  const double t{n} = {self._expr(n, scope, False)};\n"
+                scope[n] = f"t{n}"
+        stores_r = "".join(
+            f"  rr[{k}] = {self._ref(n, scope)};\n" for n, k in self.r_slot.items()
+        )
+        src.append(
+            f"struct inflx_pvec {{ double v[{max(self.n_params, 1)}]; }};\n"
+            "extern \"C\" __global__ void inflx_prologue(const inflx_pvec pv, "
+            "double* __restrict__ pc_out, double* __restrict__ rc, double of0, double dx0, "
+            "u64 row_begin, u32 n_rows) {\n"
+            "  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;\n"
+            "  const double x0 = inflx_coord(row_begin + (i < n_rows ? i : 0u), dx0, of0);\n"
+            "  (void)x0; (void)pv;\n" + body_p
+            + "  if (i == 0) {\n" + stores_p + "  }\n"
+            "  if (i >= n_rows) return;\n"
+            "  double* __restrict__ rr = rc + (u64)i * INFLX_NRF;\n  (void)rr;\n"
+            + body_r + stores_r + "}\n\n"
+        )
+
         # ---- (2b) column block as a pre-pass: one thread per (column, parameter vector) ----
         if self.cols_prepass:
             scope = {n: f"inflx_pc[pbase + {k}]" for n, k in self.p_slot.items()}

@@ -3,8 +3,10 @@
 //   g++ -O1 -ffp-contract=off -fopenmp -shared -fPIC -DINFLX_BLOCK=1 -DINFLX_RPT=<r>
 //       -DINFLX_GENERATED_CU='"<model>_<group>.cu"' tests/native/emulate.cpp -o emu.so
 // and driven through ctypes.  Mirrors the launch sequence of csrc/inflx_engine.cpp run_shard() for
-// one chunk: inflx_params -> __constant__ bank, inflx_cols (when the unit has one), inflx_rows,
-// then the grid kernel over (column tiles) x (row tiles) x (vectors).
+// one chunk: one vector -> inflx_prologue (parameters by value; P-frontier -> __constant__ bank,
+// row frontier), unless `fused` is 0; a sweep (or fused == 0) -> inflx_params -> bank, inflx_rows;
+// inflx_cols (when the unit has one); then the grid kernel over (column tiles) x (row tiles) x
+// (vectors).
 #include "cuda_host_shim.h"
 #include INFLX_GENERATED_CU
 
@@ -29,25 +31,39 @@ extern "C" int emu_info(int what) {
 // start_stop: x0_start, x0_stop, x1_start, x1_stop; rows [row_begin, row_end) of the n0-row grid.
 extern "C" int emu_grid(const double* p, unsigned n_vectors, double* out, unsigned long long n0,
                         unsigned n1, const double* start_stop, unsigned long long row_begin,
-                        unsigned long long row_end, unsigned rpt, double aux) {
+                        unsigned long long row_end, unsigned rpt, double aux, int fused) {
   const double dx0 = (start_stop[1] - start_stop[0]) / (double)n0;  // inflx_engine.cpp run_shard
   const double dx1 = (start_stop[3] - start_stop[2]) / (double)n1;
   const double of0 = start_stop[0], of1 = start_stop[2];
   const unsigned n_rows = (unsigned)(row_end - row_begin);
   if ((unsigned long long)n_vectors * (INFLX_NPF ? INFLX_NPF : 1) > INFLX_PC_CAP) return 1;
-  // (1) parameter block, straight into the constant bank
-  blockDim = {64, 1, 1};
-  for (unsigned s = 0; s < n_vectors; ++s) {
-    blockIdx = {s / 64, 0, 0};
-    threadIdx = {s % 64, 0, 0};
-    inflx_params(p, inflx_pc, n_vectors);
-  }
-  // (2) pre-passes
   std::vector<double> rc((size_t)n_vectors * n_rows * (INFLX_NRF ? INFLX_NRF : 1) + 2);
   std::vector<double> cc((size_t)n_vectors * n1 * (INFLX_NCF ? INFLX_NCF : 1) + 2);
+  const bool use_prologue = fused && n_vectors == 1;
+  if (use_prologue) {
+    // (1+2) the engine's single-vector path: every thread of ceil(n_rows / 128) CTAs
+    inflx_pvec pv = {};
+    for (int k = 0; k < INFLX_NP; ++k) pv.v[k] = p[k];
+    blockDim = {128, 1, 1};
+    const unsigned blocks = n_rows ? (n_rows + 127) / 128 : 1;
+    for (unsigned i = 0; i < blocks * 128; ++i) {
+      blockIdx = {i / 128, 0, 0};
+      threadIdx = {i % 128, 0, 0};
+      inflx_prologue(pv, inflx_pc, rc.data(), of0, dx0, row_begin, n_rows);
+    }
+  } else {
+    // (1) parameter block, straight into the constant bank
+    blockDim = {64, 1, 1};
+    for (unsigned s = 0; s < n_vectors; ++s) {
+      blockIdx = {s / 64, 0, 0};
+      threadIdx = {s % 64, 0, 0};
+      inflx_params(p, inflx_pc, n_vectors);
+    }
+  }
+  // (2) pre-passes
   blockDim = {128, 1, 1};
   for (unsigned s = 0; s < n_vectors; ++s) {
-    for (unsigned i = 0; i < n_rows; ++i) {
+    for (unsigned i = 0; i < n_rows && !use_prologue; ++i) {
       blockIdx = {i / 128, s, 0};
       threadIdx = {i % 128, 0, 0};
       inflx_rows(rc.data(), of0, dx0, row_begin, n_rows);

@@ -50,11 +50,11 @@ class Emulated:
         self.lib = ctypes.CDLL(so)
         self.lib.emu_grid.argtypes = [
             _DP, ctypes.c_uint, _DP, ctypes.c_ulonglong, ctypes.c_uint, _DP, ctypes.c_ulonglong,
-            ctypes.c_ulonglong, ctypes.c_uint, ctypes.c_double,
+            ctypes.c_ulonglong, ctypes.c_uint, ctypes.c_double, ctypes.c_int,
         ]  # fmt: skip
         self.op, self.per = op, _PER_POINT.get(op, 1)
 
-    def grid(self, p, n0, n1, ext, rows=None, rpt=16, aux=0.0):
+    def grid(self, p, n0, n1, ext, rows=None, rpt=16, aux=0.0, fused=True):
         p2 = np.ascontiguousarray(np.atleast_2d(np.asarray(p, dtype=np.float64)))
         s = p2.shape[0]
         r0, r1 = rows if rows is not None else (0, n0)
@@ -64,7 +64,7 @@ class Emulated:
             out = np.full((s, r1 - r0, n1, self.per), -7.0)  # every element must be overwritten
         ss = np.ascontiguousarray(ext, dtype=np.float64)
         rc = self.lib.emu_grid(p2.ctypes.data_as(_DP), s, out.ctypes.data_as(_DP), n0, n1,
-                               ss.ctypes.data_as(_DP), r0, r1, rpt, aux)  # fmt: skip
+                               ss.ctypes.data_as(_DP), r0, r1, rpt, aux, int(fused))  # fmt: skip
         assert rc == 0
         if self.op == "hesse":
             return out[:, 0] if np.ndim(p) == 1 else out
@@ -129,6 +129,19 @@ def test_launch_geometry_does_not_change_a_bit(model, workdir):
     # a row shard uses global coordinates
     part = emu.grid(p, n0, n1, ext, rows=(13, 40), rpt=4)
     assert _same_bits(part, base[13:40]).all()
+
+
+@pytest.mark.parametrize("model", cases.MODELS)
+def test_fused_prologue_equals_the_three_step_prologue(model, workdir):
+    """One parameter vector: `inflx_prologue` (parameters by value, parameter block recomputed by
+    every row thread) against inflx_params -> bank -> inflx_rows: not a bit of the output moves."""
+    emu = Emulated(_program(model), model, "cmp", "complete_analysis", workdir)
+    p, ext, n0, n1 = cases.params(model), cases.EXTENT[model], 150, 41  # > 128 rows: two row CTAs
+    a = emu.grid(p, n0, n1, ext, fused=True)
+    b = emu.grid(p, n0, n1, ext, fused=False)
+    assert _same_bits(a, b).all()
+    part = emu.grid(p, n0, n1, ext, rows=(129, 150), fused=True)
+    assert _same_bits(part, b[129:150]).all()
 
 
 @pytest.mark.parametrize("model", ["hyper", "d5"])
