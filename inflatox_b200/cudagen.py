@@ -643,9 +643,21 @@ class GroupProgram:
         """Statement(s) writing the result of `op` for the point with flat index `point`."""
         s, b = ("_s", ", bad") if spec else ("", "")
         if op == "complete_analysis":
+            if spec and self._v10_is_plus_zero():
+                return (
+                    f"{indent}o6 = inflx_op_complete_v10z_s({val('V')}, {val('v00')}, "
+                    f"{val('v11')}, {val('g2')}, bad);\n"
+                )
             return (
                 f"{indent}o6 = inflx_op_complete{s}({val('V')}, {val('v00')}, "
                 f"{val('v10')}, {val('v11')}, {val('g2')}{b});\n"
+            )
+        if op == "consistency_only" and spec and self._v10_is_plus_zero():
+            return f"{indent}o1 = inflx_op_consistency_v10z_s();\n"
+        if op == "consistency_rapidturn_only" and spec and self._v10_is_plus_zero():
+            return (
+                f"{indent}o1 = inflx_op_rapidturn_v10z_s({val('V')}, {val('v00')}, "
+                f"{val('v11')}, bad);\n"
             )
         if op == "consistency_only":
             return (
@@ -669,6 +681,17 @@ class GroupProgram:
                 for c, nm in enumerate(("v00", "v01", "v10", "v11"))
             )
         raise KeyError(op)
+
+    def _v10_is_plus_zero(self) -> bool:
+        """v10 (V_wv) is the compile-time constant +0.0 and no other root is a constant: the
+        complete_analysis epilogue has a closed special form (inflx_op_complete_v10z_s)."""
+        r = self.grid_roots
+        if "v10" not in r or not self.dag.is_const(r["v10"]):
+            return False
+        z = float(self.dag.cval(r["v10"]))
+        if z != 0.0 or math.copysign(1.0, z) < 0:
+            return False
+        return not any(self.klass(n) == "K" for nm, n in r.items() if nm != "v10")
 
     def _store(self, op: str, point: str, indent: str) -> str:
         if op == "complete_analysis":
@@ -738,7 +761,10 @@ class GroupProgram:
         decl = {"complete_analysis": "inflx_six o6;", "hesse": "double o4[4];"}.get(op, "double o1;")
         # a root that is a compile-time constant (hyperinflation: v10 == 0) would send EVERY point
         # of the speculative epilogue to the slow path (x/0); use the IEEE epilogue directly then
-        spec_epi = not any(self.klass(r) == "K" for r in self.grid_roots.values())
+        spec_epi = not any(self.klass(r) == "K" for r in self.grid_roots.values()) or (
+            op in ("complete_analysis", "consistency_only", "consistency_rapidturn_only")
+            and self._v10_is_plus_zero()
+        )
         return (
             f"extern \"C\" __global__ void __launch_bounds__(INFLX_BLOCK, INFLX_MIN_BLOCKS) {name}("
             "double* __restrict__ out, const double* __restrict__ rc, double of1, double dx1, "

@@ -144,3 +144,12 @@ class RawOracle(oracle.Oracle):
         fn.restype = ctypes.c_int
         assert fn(so.encode(), ctypes.byref(self.h)) == 0
         self.n_fields, self.n_params, self.meta = 2, N_PAR, {}
+
+
+# the same unit with v10 == 0: a Hesse matrix diagonal in the {v, w} basis (the README's
+# hyperinflation model has it).  complete_analysis then takes the closed special form
+# inflx_op_complete_v10z_s; irregular operands must come out as gcc's x / 0, 0 / x, inf * 0 do.
+ZERO_V10_UNIT = SPECIAL_UNIT.replace(
+    "    return (x[0] - x[1])/((x[0])*(x[0]) - 1);", "    return 0;"
+).replace('random999', 'zero_v10')
+assert "return 0;" in ZERO_V10_UNIT

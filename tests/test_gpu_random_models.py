@@ -113,3 +113,33 @@ def test_irregular_operands_take_the_exact_path(params, tmp_path):
         assert ok.all(), (k, out[..., k][~ok][:4], ref[..., k][~ok][:4])
     assert (np.isnan(out[..., 3:5]) == np.isnan(ref[..., 3:5])).all()
     assert (np.isinf(out[..., 3:5]) == np.isinf(ref[..., 3:5])).all()
+
+
+@pytest.mark.parametrize(
+    "params",
+    [[1.0, 2.0, 3.0], [1e308, 0.0, 1e-320], [np.inf, -0.0, np.nan], [3e-310, 1e300, 5e-324]],
+)
+def test_constant_zero_v10_takes_the_special_epilogue_bit_for_bit(params, tmp_path):
+    """GPU twin of the host-emulation test of the same name: a model whose v10 is the constant 0
+    (the hyperinflation model's case) never divides by that zero, and still returns gcc's bits on
+    every plane - consistency NaN everywhere, delta +0 / NaN, eta = omega * 0 - 3."""
+    from raw_units import ZERO_V10_UNIT
+
+    orc = _RawOracle(ZERO_V10_UNIT, str(tmp_path))
+    comp = Compiler.__new__(Compiler)
+    comp.nvrtc_opts = list(Compiler.default_nvrtc_flags)
+    comp.output_path = str(tmp_path / "model.c")
+    art_path = str(tmp_path / "model.bin")
+    comp.build_artifact(ZERO_V10_UNIT, art_path)
+    lib = rs.open_inflx_dylib(art_path, False)
+    lib.set_devices([0])
+    p = np.array(params, dtype=np.float64)
+    ext, n0, n1 = (-1.0, 3.0, -2.0, 2.0), 16, 32
+    out = np.zeros((n0, n1, 6))
+    rs.complete_analysis(lib, p, out, np.array(ext).reshape(2, 2), False, 0)
+    ref = orc.complete_analysis(p, n0, n1, ext)
+    assert np.isnan(out[..., 0]).all() and np.isnan(ref[..., 0]).all()
+    for k in (1, 2, 3, 4, 5):
+        ok = _bit_identical(out[..., k], ref[..., k])
+        assert ok.all(), (k, out[..., k][~ok][:4], ref[..., k][~ok][:4])
+    assert (np.isinf(out) == np.isinf(ref)).all()

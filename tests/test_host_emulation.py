@@ -224,6 +224,40 @@ def test_irregular_operands_take_the_exact_path_on_the_host(params, tmp_path):
     assert (np.isinf(out[..., 3:5]) == np.isinf(ref[..., 3:5])).all()
 
 
+@pytest.mark.parametrize(
+    "params",
+    [[1.0, 2.0, 3.0], [1e308, 0.0, 1e-320], [np.inf, -0.0, np.nan], [3e-310, 1e300, 5e-324]],
+)
+def test_constant_zero_v10_takes_the_special_epilogue_bit_for_bit(params, tmp_path):
+    """v10 == 0 (diagonal projected Hesse matrix): the generator emits inflx_op_complete_v10z_s,
+    which never divides by the zero.  Ordinary and irregular operands (zero, inf, NaN, subnormal,
+    huge in v, v00, v11, |grad V|^2): every plane that is IEEE arithmetic equals gcc's bits,
+    consistency is NaN everywhere, delta is +0 or NaN exactly where gcc says."""
+    from raw_units import ZERO_V10_UNIT
+
+    orc = RawOracle(ZERO_V10_UNIT, str(tmp_path))
+    prog = cudagen.ModelProgram(cexpr.parse_c_unit(ZERO_V10_UNIT))
+    src = prog.groups["cmp"].cuda_source("zero_v10")
+    grid = src[src.index("void __launch_bounds__(INFLX_BLOCK, INFLX_MIN_BLOCKS) inflx_grid_complete_analysis("):]
+    assert "inflx_op_complete_v10z_s(" in grid[: grid.index("if (bad.any())")]
+    p = np.array(params, dtype=np.float64)
+    ext, n0, n1 = (-1.0, 3.0, -2.0, 2.0), 16, 32
+    out = Emulated(prog, "zero_v10", "cmp", "complete_analysis", tmp_path).grid(p, n0, n1, ext)
+    ref = orc.complete_analysis(p, n0, n1, ext)
+    assert np.isnan(out[..., 0]).all() and np.isnan(ref[..., 0]).all()
+    for k in (1, 2, 3, 4, 5):  # no atan / tan evaluation is left: eta and delta are exact too
+        ok = _same_bits(out[..., k], ref[..., k])
+        assert ok.all(), (k, out[..., k][~ok][:4], ref[..., k][~ok][:4])
+    assert (np.isnan(out) == np.isnan(ref)).all() and (np.isinf(out) == np.isinf(ref)).all()
+    c1 = Emulated(prog, "zero_v10", "con", "consistency_only", tmp_path).grid(p, n0, n1, ext)
+    assert np.isnan(c1).all() and np.isnan(orc.consistency_only(p, n0, n1, ext)).all()
+    rt = Emulated(prog, "zero_v10", "con", "consistency_rapidturn_only", tmp_path).grid(p, n0, n1, ext)
+    ref_rt = orc.consistency_rapidturn_only(p, n0, n1, ext)
+    assert _same_bits(rt, ref_rt).all(), (rt[~_same_bits(rt, ref_rt)][:4], ref_rt[~_same_bits(rt, ref_rt)][:4])
+    if params == [1.0, 2.0, 3.0]:
+        assert (rt == 1.0).any() and np.isnan(rt).any()
+
+
 TRANSCENDENTAL_UNIT = """
 double V(const double x[], const double args[]){
     return exp(-x[0]*x[1])*cos(x[0] + x[1]) + args[0]*log(2 + x[0]*x[0]*x[1]*x[1]) + pow(1 + x[0]*x[0], args[1]);

@@ -22,9 +22,10 @@ ROWS = [
     ("issue slots busy %", "smsp__issue_active.avg.pct_of_peak_sustained_active"),
     ("DRAM written", "dram__bytes_write.sum"),
     ("DRAM read", "dram__bytes_read.sum"),
-    ("L2 write sectors (32 B)", "lts__t_sectors_op_write.sum"),
-    ("local-memory (spill) store sectors", "l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum"),
+    ("bytes written L1 -> L2 (output + spill stores)", "l1tex__m_l1tex2xbar_write_bytes.sum"),
+    ("local-memory (spill) store sectors (32 B)", "l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum"),
     ("local-memory (spill) load sectors", "l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum"),
+    ("... of which missed L1 (reloaded from L2)", "l1tex__t_sectors_pipe_lsu_mem_local_op_ld_lookup_miss.sum"),
     ("warp instructions executed", "smsp__inst_executed.sum"),
     ("stall: wait / issue", "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio"),
     ("stall: math pipe throttle / issue", "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio"),
