@@ -158,12 +158,15 @@ class GroupProgram:
     """
 
     def __init__(self, dag: Dag, roots: ModelRoots, group: str, n_params: int, libm: str = "glibc",
-                 cols: str = "auto"):
+                 cols: str = "auto", store: str = "auto"):
         if libm not in LIBM_FLAVOURS:
             raise Exception(f"unknown libm flavour {libm!r}: one of {LIBM_FLAVOURS}")
         if cols not in ("auto", "always", "never"):
             raise Exception(f"unknown column pre-pass mode {cols!r}: auto, always or never")
         self.cols = cols
+        if store not in ("auto", "transposed", "direct"):
+            raise Exception(f"unknown store mode {store!r}: auto, transposed or direct")
+        self.store = store
         self.dag = dag
         self.group = group
         self.n_params = n_params
@@ -308,12 +311,32 @@ class GroupProgram:
             )
         ]
         self.c_frontier = self.c_live if self.cols_prepass else []
+        # complete_analysis kernels with very little arithmetic per 48-byte record are bound by the
+        # L1 -> L2 store path, not by issue slots: they use the warp-transposed store
+        # (inflx_store6_warp).  Estimate: ~2.5 issue cycles per FP64 instruction (tools/sass_cost.py)
+        # against the ~270 cycles per warp and row the HBM write roof allows.
+        self.transposed_store = self.group == "cmp" and (
+            self.store == "transposed"
+            or (self.store == "auto" and self._estimated_fp64_per_point() * 2.5 < 270)
+        )
         self.min_blocks = MIN_BLOCKS.get(self.group, 5)
         while self.min_blocks > 4 and 2 * len(self.c_live) + WORKING_REGS > REGS_AT[self.min_blocks]:
             self.min_blocks -= 1
         self.c_slot = {n: k for k, n in enumerate(self.c_frontier)}
         # rows of the row-frontier array are read with 128-bit loads: keep them 16-byte aligned
         self.n_row_slots = (len(self.r_frontier) + 1) & ~1
+
+    def _estimated_fp64_per_point(self) -> int:
+        """Rough FP64 instruction count of one grid point of complete_analysis: class-M operations
+        (a quotient 3, its own reciprocal 5, a square root 9) + the epilogue (160; 60 in the closed
+        form for a constant-zero v10)."""
+        n = 0
+        for i in self.nodes_of("M", self.grid_nodes):
+            k = self.node(i)[0]
+            n += {"/": 3, "rcp": 5}.get(k, 1)
+            if k == "f":
+                n += 8 if self.node(i)[1] == "sqrt" else 20
+        return n + (60 if self._v10_is_plus_zero() else 160)
 
     def _hoisted_libm(self, i: int) -> str | None:
         """Prefix of the out-of-line libm function ("inflx_gl_" / "inflx_cr_") the call node `i` is
@@ -381,6 +404,7 @@ class GroupProgram:
             "n_c_frontier": len(self.c_frontier),
             "n_c_live": len(self.c_live),
             "min_blocks": self.min_blocks,
+            "transposed_store": self.transposed_store,
         }
 
     # -- emission ----------------------------------------------------------------------------
@@ -759,6 +783,7 @@ class GroupProgram:
             return f"roots[{order.index(rname)}]"
 
         decl = {"complete_analysis": "inflx_six o6;", "hesse": "double o4[4];"}.get(op, "double o1;")
+        transposed = op == "complete_analysis" and self.transposed_store
         # a root that is a compile-time constant (hyperinflation: v10 == 0) would send EVERY point
         # of the speculative epilogue to the slow path (x/0); use the IEEE epilogue directly then
         spec_epi = not any(self.klass(r) == "K" for r in self.grid_roots.values()) or (
@@ -791,14 +816,19 @@ class GroupProgram:
             "      rsm[k] = __ldg(src + k);\n"
             "  }\n"
             "#endif\n"
-            "  const bool active = col < n1;\n"
+            + ("  __shared__ double2 inflx_st[(INFLX_BLOCK + 31) / 32][96];\n" if transposed else "")
+            + "  const bool active = col < n1;\n"
             "  const double x1 = inflx_coord(active ? col : 0u, dx1, of1);\n"
             "  inflx_chk bad_c;\n"
             "  (void)x1; (void)aux; (void)comp_stride; (void)rc; (void)pbase; (void)cc;\n"
             + col_block
             + "#if INFLX_NRF > 0\n  __syncthreads();\n#endif\n"
-            "  if (!active) return;\n"
-            "#pragma unroll 1\n"
+            # transposed stores are a warp-wide operation: lanes beyond the grid's last column keep
+            # computing (on column 0) and are masked out of the store instead of leaving
+            + ("  const u32 warp_col0 = col - (threadIdx.x & 31u);\n"
+               "  const u32 n_valid = warp_col0 < n1 ? min(32u, n1 - warp_col0) : 0u;\n"
+               if transposed else "  if (!active) return;\n")
+            + "#pragma unroll 1\n"
             "  for (u32 j = 0; j < rows_here; ++j) {\n"
             "    const u64 rowid = (u64)s * n_rows + r0 + j;\n"
             "#if defined(INFLX_EXPERIMENT_NO_SMEM)\n"
@@ -818,20 +848,19 @@ class GroupProgram:
             # the speculative result is stored as soon as it exists (its registers are free before
             # the validity flag is final) and overwritten by the rare recomputation;
             # -DINFLX_LATE_STORE: one store after the flag is known (round 1)
-            + "#ifndef INFLX_LATE_STORE\n"
-            + self._store(op, "point", "    ")
-            + "#endif\n"
+            + ("" if transposed else "#ifndef INFLX_LATE_STORE\n" + self._store(op, "point", "    ") + "#endif\n")
             + "    if (bad.any()) {  // rare: redo this point with the IEEE operators\n"
             f"      double roots[{len(order)}];\n"
             "      inflx_slow_roots(rr, x1, pbase, roots);\n"
             + self._epilogue(op, slow_val, "point", "      ", False)
-            + "#ifndef INFLX_LATE_STORE\n"
-            + self._store(op, "point", "      ")
-            + "#endif\n"
+            + ("" if transposed else "#ifndef INFLX_LATE_STORE\n" + self._store(op, "point", "      ") + "#endif\n")
             + "    }\n"
-            + "#ifdef INFLX_LATE_STORE\n"
-            + self._store(op, "point", "    ")
-            + "#endif\n"
+            + (
+                "    inflx_store6_warp(out, rowid * n1 + warp_col0, n_valid, o6, "
+                "inflx_st[threadIdx.x >> 5]);\n"
+                if transposed
+                else "#ifdef INFLX_LATE_STORE\n" + self._store(op, "point", "    ") + "#endif\n"
+            )
             + "  }\n}\n\n"
         )
 
@@ -937,7 +966,8 @@ class GroupProgram:
 class ModelProgram:
     """All groups of one model + the metadata the artefact header carries."""
 
-    def __init__(self, unit: ParsedUnit, libm: str = "glibc", cols: str = "auto"):
+    def __init__(self, unit: ParsedUnit, libm: str = "glibc", cols: str = "auto",
+                 store: str = "auto"):
         self.libm = libm
         if unit.dim != 2:
             raise Exception(
@@ -946,7 +976,7 @@ class ModelProgram:
         self.unit = unit
         self.roots = ModelRoots(unit)
         self.groups = {
-            g: GroupProgram(unit.dag, self.roots, g, unit.n_parameters or 0, libm, cols)
+            g: GroupProgram(unit.dag, self.roots, g, unit.n_parameters or 0, libm, cols, store)
             for g in GROUPS
         }
 

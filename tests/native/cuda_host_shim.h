@@ -29,6 +29,7 @@ struct inflx_emu_dim3 {
 };
 static thread_local inflx_emu_dim3 blockIdx, threadIdx, blockDim, gridDim;
 static inline void __syncthreads() {}
+static inline void __syncwarp() {}
 
 struct alignas(16) double2 {
   double x, y;

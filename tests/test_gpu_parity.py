@@ -313,7 +313,7 @@ def test_basis_validation():
     import inflatox_b200 as ix
 
     # a sound basis passes (possibly with out-of-domain warnings, as upstream)
-    rs.open_inflx_dylib(cases.artifact("angular").shared_object_path, True)
+    cases.load_checked(lambda: rs.open_inflx_dylib(cases.artifact("angular").shared_object_path, True))
     # a basis whose first vector is not normalised must be refused (reference src/lib.rs:171-173)
     m = cases.load_model("doc")
     m.basis[0] = [2 * c for c in m.basis[0]]
@@ -348,7 +348,7 @@ def test_reference_test_flows_through_the_facade(model):
     same return shapes; plus the oracle on what they return."""
     from inflatox_b200.consistency_conditions import GeneralisedAL
 
-    anguelova = GeneralisedAL(cases.artifact(model))
+    anguelova = cases.load_checked(lambda: GeneralisedAL(cases.artifact(model)))
     args, extent = cases.params(model), cases.EXTENT[model]
     N = 100
     orc = oracle.Oracle(model)

@@ -45,11 +45,17 @@ def _run_reference_test(name: str, timeout: int) -> None:
         [site, cases.ROOT] + [p for p in [env.get("PYTHONPATH")] if p] + [os.path.join(site, "_stubs")]
     )
     env.setdefault("INFLATOX_CACHE_DIR", os.path.join(cases.ROOT, "tests", ".cubin_cache"))
-    r = subprocess.run(
-        [sys.executable, "-m", "pytest", os.path.join(site, "reference_tests", name), "-q", "-x",
-         "-p", "no:cacheprovider", "--rootdir", os.path.join(site, "reference_tests")],
-        capture_output=True, text=True, timeout=timeout, env=env, cwd=site,
-    )  # fmt: skip
+    for attempt in range(4):
+        r = subprocess.run(
+            [sys.executable, "-m", "pytest", os.path.join(site, "reference_tests", name), "-q", "-x",
+             "-p", "no:cacheprovider", "--rootdir", os.path.join(site, "reference_tests")],
+            capture_output=True, text=True, timeout=timeout, env=env, cwd=site,
+        )  # fmt: skip
+        # the reference's load-time basis check draws RANDOM parameters (src/lib.rs:142-203) and
+        # fails in ~8 % of the loads of the angular model on the reference's own CPU path as well
+        # (tests/test_oracle.py): that upstream flake, and only that, is retried
+        if r.returncode == 0 or "Expected basis vector" not in r.stdout + r.stderr:
+            break
     assert r.returncode == 0, f"{name}\n{r.stdout[-3000:]}\n{r.stderr[-3000:]}"
     assert " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-500:]
 

@@ -47,6 +47,8 @@ def main():
             comp.libm = v["libm"]
         if "cols" in v:
             comp.cols_prepass = v["cols"]
+        if "store" in v:
+            comp.store_mode = v["store"]
         art = comp.compile()
         lib = rs.open_inflx_dylib(art.shared_object_path, False)
         lib.set_devices([0])

@@ -42,6 +42,8 @@ def main():
                 comp.libm = v["libm"]
             if "cols" in v:
                 comp.cols_prepass = v["cols"]
+            if "store" in v:
+                comp.store_mode = v["store"]
             art = comp.compile()
         except Exception as e:
             print(v, "compile failed", str(e)[:200])
