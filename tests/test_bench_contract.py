@@ -57,3 +57,19 @@ def test_default_workload_is_the_metrics_config():
     # args order of the hyperinflation model is (m, phi0, L): BASELINE C5's ranges per column
     assert p[:, 0].min() >= 1e-3 and p[:, 0].max() <= 10 and abs(p[:, 1]).max() <= 1
     assert p[:, 2].min() >= 0.05 and p[:, 2].max() <= 2.0
+
+
+def test_every_baseline_config_and_every_repo_model_has_a_bench_config():
+    """BASELINE.json's five configs + complete_analysis on a 16384^2 grid for each remaining repo test
+    model (north_star: ">= 50 % of the FP64 roofline ... for each repo test model"): the default
+    `python bench.py` run reports all of them under `configs` next to the C3 headline."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(cases.ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert sorted(bench.CONFIGS) == ["C1", "C2", "C3", "C4", "C5", "C6", "C7", "C8"]
+    full = {bench.CONFIGS[c][0] for c in bench.CONFIGS
+            if bench.CONFIGS[c][1:4] == ("complete_analysis", 16384, 16384)}
+    assert full == {"egno", "d5", "angular", "hyper", "doc"} == set(cases.MODELS)
+    assert bench.CPU_CONTRACT == "fast"  # the faster CPU build is the baseline

@@ -374,6 +374,11 @@ def test_reference_test_flows_through_the_facade(model):
     assert flags.dtype == bool and flags.shape == (N, N)
     h = anguelova.calc_H_array(args, [extent[0], extent[2]], [extent[1], extent[3]], [N, N])
     assert h.shape == (2, 2, N, N)
+    # the reference's own signature (consistency_conditions.py:119-127): scalars per axis, N last
+    h_ref_sig = anguelova.calc_H_array(args, extent[0], extent[1], extent[2], extent[3], [N, N])
+    assert np.array_equal(h, h_ref_sig, equal_nan=True)
+    with pytest.raises(TypeError):
+        anguelova.calc_H_array(args, extent[0], extent[1])
     if model == "d5":
         # the reference walks the axes from `stop` outwards (src/lib.rs:250-258); for d5 that leaves
         # the model's domain, where w1 degenerates into v - the reference-generated C says the
