@@ -831,9 +831,7 @@ class GroupProgram:
             + "#pragma unroll 1\n"
             "  for (u32 j = 0; j < rows_here; ++j) {\n"
             "    const u64 rowid = (u64)s * n_rows + r0 + j;\n"
-            "#if defined(INFLX_EXPERIMENT_NO_SMEM)\n"
-            "    const double2* __restrict__ rr = reinterpret_cast<const double2*>(rc + rowid * INFLX_NRF);\n"
-            "#elif INFLX_NRF > 0\n"
+            "#if INFLX_NRF > 0\n"
             "    const double2* __restrict__ rr = rsm + j * (INFLX_NRF / 2);\n"
             "#else\n"
             "    const double2* __restrict__ rr = nullptr;\n"

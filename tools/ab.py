@@ -4,7 +4,7 @@ times each variant once (device-resident output, CUDA events around the grid ker
 thermal drift hits all variants alike; reports the median over the rounds and the ratio to the
 first variant.
 
-    python tools/ab.py egno complete_analysis 16384 '[{"name": "base"}, {"name": "rcp4", "extra": ["-DINFLX_EXPERIMENT_RCP4"]}]' [rounds]
+    python tools/ab.py egno complete_analysis 16384 '[{"name": "base"}, {"name": "rcp5", "extra": ["-DINFLX_RCP_NVCC"]}]' [rounds]
 
 Variant keys: name, rpt (16), block (128), minb, fmad, extra (NVRTC flags), libm, cols, run_rpt."""
 import json

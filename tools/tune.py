@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Kernel-only timing of compile-time variants (rows per thread, CTA width, register cap, fmad)
-of the grid kernel on a GPU box.  Usage: python tools/tune.py egno complete_analysis 8192 ['[{"rpt": 16, "block": 128, "minb": 5, "extra": ["-DINFLX_EXPERIMENT_RCP4"], "libm": "glibc-all"}]']"""
+of the grid kernel on a GPU box.  Usage: python tools/tune.py egno complete_analysis 8192 ['[{"rpt": 16, "block": 128, "minb": 5, "extra": ["-DINFLX_RCP_NVCC"], "libm": "glibc-all"}]']"""
 import itertools
 import json
 import os
