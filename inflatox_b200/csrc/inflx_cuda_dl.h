@@ -27,7 +27,7 @@
   X(cuEventRecord) X(cuEventSynchronize) X(cuEventElapsedTime) X(cuEventDestroy)                \
   X(cuLaunchKernel) X(cuGetErrorString) X(cuGetErrorName) X(cuPointerGetAttribute)              \
   X(cuMemGetInfo) X(cuMemHostRegister) X(cuMemHostUnregister) X(cuMemHostGetDevicePointer)    \
-  X(cuCtxGetCurrent) X(cuDeviceGetPCIBusId)
+  X(cuCtxGetCurrent) X(cuDeviceGetPCIBusId) X(cuOccupancyMaxActiveBlocksPerMultiprocessor)
 
 #define INFLX_NVRTC_FUNCS(X)                                                                    \
   X(nvrtcCreateProgram) X(nvrtcDestroyProgram) X(nvrtcCompileProgram) X(nvrtcGetProgramLogSize) \

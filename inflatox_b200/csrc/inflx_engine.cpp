@@ -312,7 +312,10 @@ struct GroupModule {
   CUmodule mod = nullptr;
   CUdeviceptr pc_sym = 0;
   CUfunction params = nullptr, rows = nullptr, cols = nullptr, prologue = nullptr;
+  bool tail_tiles = false;  // grid kernels take (n_big, rpt_tail): two tile heights per launch
+  uint32_t tail_div = 0;    // the generator's advice: tail tiles of rpt / tail_div rows (0: none)
   std::map<std::string, CUfunction> fns;
+  std::map<CUfunction, int> resident;  // CTAs per SM of a grid kernel (occupancy query, cached)
 };
 
 struct inflx_lib {
@@ -355,6 +358,16 @@ static inflx_status load_module(inflx_lib* lib, DeviceState* dev, const char* gr
   if (g->ncf) CU_TRY(cu.p_cuModuleGetFunction(&gm->cols, gm->mod, "inflx_cols"));
   if (cu.p_cuModuleGetFunction(&gm->prologue, gm->mod, "inflx_prologue") != CUDA_SUCCESS)
     gm->prologue = nullptr;  // artefact of an older generator: the three-step prologue is used
+  {
+    CUdeviceptr marker = 0;
+    size_t mbytes = 0;
+    gm->tail_tiles =
+        cu.p_cuModuleGetGlobal(&marker, &mbytes, gm->mod, "inflx_has_tail_tiles") == CUDA_SUCCESS;
+    if (gm->tail_tiles && mbytes == sizeof(uint32_t)) {
+      CU_TRY(cu.p_cuMemcpyDtoHAsync(&gm->tail_div, marker, sizeof(uint32_t), dev->compute));
+      CU_TRY(cu.p_cuStreamSynchronize(dev->compute));
+    }
+  }
   *out = gm.get();
   lib->modules[key] = std::move(gm);
   return INFLX_OK;
@@ -656,10 +669,50 @@ static inflx_status run_shard(inflx_lib* lib, const inflx_grid_request& rq, cons
         while (rpt > 2 && ctas(rpt) < 4 * wave) rpt /= 2;
       }
       while (rpt < RPT && (rc + rpt - 1) / rpt > 65535) rpt *= 2;  // gridDim.y limit
+      // Two tile heights (tools/shard_probe.py, profiles/shard_probe_r2.txt): CTAs are dispatched
+      // in blockIdx order and all of a wave take the same time, so a launch of uniform tiles ends
+      // with the machine draining for about one full tile's duration - 1.5-3 % of a 2048-row
+      // shard (one of 8 GPUs on C3), whatever the tile height, because shorter tiles pay the
+      // column block more often.  The last ~1.5 waves' worth of rows therefore go out as tiles of
+      // a quarter of the height: the drain shrinks with them, the extra column blocks touch a few
+      // per cent of the rows.  Single grids only: in a sweep (blockIdx.z = vector) only the last
+      // vector's tiles are the launch's tail.
+      uint32_t rpt_tail = rpt, n_big = (uint32_t)(rc / rpt);
+      if (gm->tail_tiles && sc == 1 && rpt >= 4) {
+        uint32_t want_tail = gm->tail_div ? std::max<uint32_t>(2, rpt / gm->tail_div) : 0;
+        if (const char* e = getenv("INFLATOX_RPT_TAIL"))
+          want_tail = (uint32_t)std::min<long>(std::max<long>(atol(e), 0), rpt);
+        if (want_tail && want_tail < rpt) {
+          int per_sm = 0;
+          {
+            std::lock_guard<std::mutex> lk(lib->mu);
+            auto it = gm->resident.find(grid_fn);
+            if (it != gm->resident.end()) {
+              per_sm = it->second;
+            } else {
+              if (cu.p_cuOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grid_fn, (int)BLOCK,
+                                                                   0) != CUDA_SUCCESS ||
+                  per_sm < 1)
+                per_sm = 4;
+              gm->resident[grid_fn] = per_sm;
+            }
+          }
+          const uint64_t slots = (uint64_t)dev->sm_count * per_sm;
+          const uint64_t tail_tiles = (3 * slots / 2 + col_tiles - 1) / col_tiles;  // of `rpt` rows
+          const uint64_t big = rc / rpt;
+          const uint64_t nb = big > tail_tiles ? big - tail_tiles : 0;
+          const uint64_t y = nb + (rc - nb * rpt + want_tail - 1) / want_tail;
+          if (y <= 65535) {
+            n_big = (uint32_t)nb;
+            rpt_tail = want_tail;
+          }
+        }
+      }
+      const uint64_t grid_y = n_big + (rc - (uint64_t)n_big * rpt + rpt_tail - 1) / rpt_tail;
       void* args[] = {&outp, &dev->d_rc.ptr, &of1, &dx1, &n1u, &n_rows, &comp_stride, &aux, &rpt,
-                      &dev->d_cc.ptr};
-      if ((st = launch(cu, grid_fn, (unsigned)col_tiles, (unsigned)((rc + rpt - 1) / rpt),
-                       (unsigned)sc, BLOCK, cs, args)))
+                      &dev->d_cc.ptr, &n_big, &rpt_tail};
+      if ((st = launch(cu, grid_fn, (unsigned)col_tiles, (unsigned)grid_y, (unsigned)sc, BLOCK, cs,
+                       args)))
         return st;
       res.launches++;
       if (to_device) CU_TRY(cu.p_cuEventRecord(dev->ev_g1, cs));

@@ -543,7 +543,12 @@ class GroupProgram:
         src.append(f"#define INFLX_NRF {nrf}\n#define INFLX_PC_CAP {PC_CAPACITY}\n")
         src.append(f"#define INFLX_NCF {len(self.c_frontier)}\n")
         src.append(f"#define INFLX_SCALAR_XS {(self.n_params + 1) & ~1}\n")
-        src.append("__constant__ double inflx_pc[INFLX_PC_CAP];\n\n")
+        src.append("__constant__ double inflx_pc[INFLX_PC_CAP];\n")
+        # feature marker the engine looks up: the grid kernels take (n_big, rpt_tail).  Its value is
+        # the generator's advice: tail tiles of rpt / value rows; 0 = uniform tiles (a kernel bound
+        # by the memory system gains nothing from a shorter drain and pays for the short tiles)
+        tail_div = 0 if (self.group == "cmp" and self.transposed_store) else 4
+        src.append(f'extern "C" __device__ const unsigned inflx_has_tail_tiles = {tail_div};\n\n')
 
         # ---- (1) parameter block: one thread per parameter vector ----
         scope = self._leaf_scope({("p", k): f"p[{k}]" for k in range(self.n_params)})
@@ -794,16 +799,20 @@ class GroupProgram:
             f"extern \"C\" __global__ void __launch_bounds__(INFLX_BLOCK, INFLX_MIN_BLOCKS) {name}("
             "double* __restrict__ out, const double* __restrict__ rc, double of1, double dx1, "
             "u32 n1, u32 n_rows, u64 comp_stride, double aux, u32 rpt, "
-            "const double* __restrict__ cc) {\n"
+            "const double* __restrict__ cc, u32 n_big, u32 rpt_tail) {\n"
             "  const u32 col = blockIdx.x * INFLX_BLOCK + threadIdx.x;\n"
             + (
                 "  const u32 s = blockIdx.z;\n  const u32 pbase = s * INFLX_NPF;\n"
                 if sweep
                 else "  const u32 s = 0;\n  const u32 pbase = 0;\n"
             )
-            # rows per CTA: chosen per launch by the engine (<= INFLX_RPT, which sizes the smem)
-            + "  const u32 r0 = blockIdx.y * rpt;\n"
-            "  const u32 rows_here = min(rpt, n_rows - r0);\n"
+            # rows per CTA: chosen per launch by the engine (<= INFLX_RPT, which sizes the smem).
+            # Two tile heights: the first n_big row tiles walk `rpt` rows, the rest `rpt_tail`
+            # (<= rpt) - CTAs are dispatched in blockIdx order, so the launch ENDS on short CTAs
+            # and the last wave drains in a fraction of a full tile's duration.
+            + "  const bool tail = blockIdx.y >= n_big;\n"
+            "  const u32 r0 = tail ? n_big * rpt + (blockIdx.y - n_big) * rpt_tail : blockIdx.y * rpt;\n"
+            "  const u32 rows_here = min(tail ? rpt_tail : rpt, n_rows - r0);\n"
             # the CTA's rows of the row-frontier array: one cooperative, coalesced 128-bit copy
             # into shared memory, overlapped with the column block; per-point reads are then
             # conflict-free LDS.128 broadcasts instead of exposed L2 round trips

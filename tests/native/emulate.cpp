@@ -6,7 +6,7 @@
 // one chunk: one vector -> inflx_prologue (parameters by value; P-frontier -> __constant__ bank,
 // row frontier), unless `fused` is 0; a sweep (or fused == 0) -> inflx_params -> bank, inflx_rows;
 // inflx_cols (when the unit has one); then the grid kernel over (column tiles) x (row tiles) x
-// (vectors).
+// (vectors), with the engine's two tile heights (n_big tiles of rpt rows, the rest rpt_tail).
 #include "cuda_host_shim.h"
 #include INFLX_GENERATED_CU
 
@@ -31,7 +31,8 @@ extern "C" int emu_info(int what) {
 // start_stop: x0_start, x0_stop, x1_start, x1_stop; rows [row_begin, row_end) of the n0-row grid.
 extern "C" int emu_grid(const double* p, unsigned n_vectors, double* out, unsigned long long n0,
                         unsigned n1, const double* start_stop, unsigned long long row_begin,
-                        unsigned long long row_end, unsigned rpt, double aux, int fused) {
+                        unsigned long long row_end, unsigned rpt, double aux, int fused,
+                        unsigned n_big, unsigned rpt_tail) {
   const double dx0 = (start_stop[1] - start_stop[0]) / (double)n0;  // inflx_engine.cpp run_shard
   const double dx1 = (start_stop[3] - start_stop[2]) / (double)n1;
   const double of0 = start_stop[0], of1 = start_stop[2];
@@ -77,7 +78,10 @@ extern "C" int emu_grid(const double* p, unsigned n_vectors, double* out, unsign
 #endif
   }
   // (3) grid kernel, one emulated thread per CTA (INFLX_BLOCK == 1)
-  const unsigned row_tiles = (n_rows + rpt - 1) / rpt;
+  // two tile heights as in run_shard: n_big tiles of rpt rows, then tiles of rpt_tail rows
+  if (rpt_tail == 0 || rpt_tail > rpt) rpt_tail = rpt;
+  if ((unsigned long long)n_big * rpt > n_rows) n_big = n_rows / rpt;
+  const unsigned row_tiles = n_big + (n_rows - n_big * rpt + rpt_tail - 1) / rpt_tail;
   const unsigned long long comp_stride = (unsigned long long)n_vectors * n_rows * n1;
 #pragma omp parallel for collapse(2) schedule(dynamic, 8)
   for (unsigned rt = 0; rt < row_tiles; ++rt)
@@ -88,9 +92,10 @@ extern "C" int emu_grid(const double* p, unsigned n_vectors, double* out, unsign
         blockIdx = {c, rt, s};
         if (n_vectors > 1)
           INFLX_EMU_KERNEL_SWEEP(out, rc.data(), of1, dx1, n1, n_rows, comp_stride, aux, rpt,
-                                 cc.data());
+                                 cc.data(), n_big, rpt_tail);
         else
-          INFLX_EMU_KERNEL(out, rc.data(), of1, dx1, n1, n_rows, comp_stride, aux, rpt, cc.data());
+          INFLX_EMU_KERNEL(out, rc.data(), of1, dx1, n1, n_rows, comp_stride, aux, rpt, cc.data(),
+                           n_big, rpt_tail);
       }
   return 0;
 }

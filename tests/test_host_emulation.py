@@ -50,11 +50,12 @@ class Emulated:
         self.lib = ctypes.CDLL(so)
         self.lib.emu_grid.argtypes = [
             _DP, ctypes.c_uint, _DP, ctypes.c_ulonglong, ctypes.c_uint, _DP, ctypes.c_ulonglong,
-            ctypes.c_ulonglong, ctypes.c_uint, ctypes.c_double, ctypes.c_int,
+            ctypes.c_ulonglong, ctypes.c_uint, ctypes.c_double, ctypes.c_int, ctypes.c_uint,
+            ctypes.c_uint,
         ]  # fmt: skip
         self.op, self.per = op, _PER_POINT.get(op, 1)
 
-    def grid(self, p, n0, n1, ext, rows=None, rpt=16, aux=0.0, fused=True):
+    def grid(self, p, n0, n1, ext, rows=None, rpt=16, aux=0.0, fused=True, n_big=None, rpt_tail=0):
         p2 = np.ascontiguousarray(np.atleast_2d(np.asarray(p, dtype=np.float64)))
         s = p2.shape[0]
         r0, r1 = rows if rows is not None else (0, n0)
@@ -64,7 +65,8 @@ class Emulated:
             out = np.full((s, r1 - r0, n1, self.per), -7.0)  # every element must be overwritten
         ss = np.ascontiguousarray(ext, dtype=np.float64)
         rc = self.lib.emu_grid(p2.ctypes.data_as(_DP), s, out.ctypes.data_as(_DP), n0, n1,
-                               ss.ctypes.data_as(_DP), r0, r1, rpt, aux, int(fused))  # fmt: skip
+                               ss.ctypes.data_as(_DP), r0, r1, rpt, aux, int(fused),
+                               0xFFFFFFFF if n_big is None else n_big, rpt_tail)  # fmt: skip
         assert rc == 0
         if self.op == "hesse":
             return out[:, 0] if np.ndim(p) == 1 else out
@@ -126,6 +128,10 @@ def test_launch_geometry_does_not_change_a_bit(model, workdir):
     base = emu.grid(p, n0, n1, ext, rpt=16)
     for rpt in (1, 2, 5, 8):  # rows per CTA: the engine's launch argument
         assert _same_bits(emu.grid(p, n0, n1, ext, rpt=rpt), base).all(), rpt
+    # two tile heights: n_big full tiles, then short ones (the engine's tail policy)
+    for rpt, n_big, rpt_tail in ((16, 1, 4), (16, 2, 2), (8, 0, 3), (8, 5, 1), (16, 0, 16)):
+        got = emu.grid(p, n0, n1, ext, rpt=rpt, n_big=n_big, rpt_tail=rpt_tail)
+        assert _same_bits(got, base).all(), (rpt, n_big, rpt_tail)
     # a row shard uses global coordinates
     part = emu.grid(p, n0, n1, ext, rows=(13, 40), rpt=4)
     assert _same_bits(part, base[13:40]).all()
