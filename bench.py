@@ -342,19 +342,20 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
     achieved_gbs = my_points * per * 8 / per_launch_s / 1e9
-    traffic = None
+    traffic_db = {}
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as fh:
-            traffic = json.load(fh).get(f"{a.config}")
-        if traffic is not None:  # captured at N=1: per-launch traffic scales with the shard
-            traffic = traffic * my_points / total_points
+            traffic_db = json.load(fh)
+    traffic = traffic_db.get(f"{a.config}")
+    if traffic is not None:  # captured at N=1: per-launch traffic scales with the shard
+        traffic = traffic * my_points / total_points
+    traffic_note = ("profiles/ncu_traffic.json: dram bytes of one `ncu --set full` capture of this "
+                    "kernel (committed, scaled to this rank's shard) - NOT measured in this run")
     roofline = {
         "bound": "fp64", "kernel": f"inflx_grid_{op}", "achieved": achieved_tf, "peak": fp64_peak,
         "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak, "traffic": traffic,
-        "traffic_source": None if traffic is None else "profiles/ncu_traffic.json: dram bytes of one "
-        "`ncu --set full` capture of this kernel (committed, scaled to this rank's shard) - NOT "
-        "measured in this run",
+        "traffic_source": None if traffic is None else traffic_note,
         "flops_per_point": F, "points_per_launch": my_points,
         "peak_source": "DFMA micro-kernel measured in this run (inflx_measure_fp64_peak; "
         f"median {med.value:.2f}); MEASURED_PEAKS.json has no fp64 entry",
@@ -449,7 +450,8 @@ def main():
             "ms_per_step": t_all / steps, "dominant_kernel_ms_per_step": t_grid / steps,
             "roofline": {"bound": "fp64", "kernel": f"inflx_grid_{c_op}", "achieved": tf,
                          "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
-                         "flops_per_point": c_F},
+                         "flops_per_point": c_F, "traffic": traffic_db.get(cfg),
+                         "traffic_source": traffic_note if cfg in traffic_db else None},
             "roofline_hbm": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
                              "frac": gbs / hbm_peak, "bytes_per_point": c_per * 8},
         }  # fmt: skip

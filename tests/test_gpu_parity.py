@@ -172,6 +172,33 @@ def test_device_resident_output_equals_host_output(setup):
     assert np.array_equal(d.cpu().numpy().reshape(N0, N1, 6), host, equal_nan=True)
 
 
+def test_tail_tiles_do_not_change_a_bit(setup, monkeypatch):
+    """One launch with two tile heights (the engine's default: the last ~1.5 waves of rows on
+    quarter-height tiles) against uniform tiles and against other forced heights, on a ragged
+    8190 x 1000 grid in ONE launch (device-resident), where both kinds of tile occur."""
+    import torch
+
+    m, lib, orc, p, ext = setup
+    n0, n1 = 8190, 1000
+    d = torch.empty(n0 * n1 * 6, dtype=torch.float64, device="cuda:0")
+
+    def run():
+        d.fill_(-7.0)
+        rep = rs.grid_eval(lib, "complete_analysis", p, None, n0, n1, ext, device=0,
+                           out_device_ptr=d.data_ptr())  # fmt: skip
+        assert rep["launches"] <= 3
+        return d.cpu().numpy().view(np.uint64).copy()
+
+    monkeypatch.setenv("INFLATOX_RPT_TAIL", "0")
+    uniform = run()
+    monkeypatch.delenv("INFLATOX_RPT_TAIL")
+    assert np.array_equal(run(), uniform)
+    for rpt, tail in ((16, 4), (16, 1), (8, 3), (4, 2)):
+        monkeypatch.setenv("INFLATOX_RPT", str(rpt))
+        monkeypatch.setenv("INFLATOX_RPT_TAIL", str(tail))
+        assert np.array_equal(run(), uniform), (rpt, tail)
+
+
 @pytest.mark.parametrize("model", ["angular", "egno", "d5"])
 def test_on_trajectory(model):
     """The trajectories the reference's own tests evaluate (tests/test_angular.py:79-83,
