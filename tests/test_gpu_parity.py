@@ -206,14 +206,19 @@ def test_tail_tiles_do_not_change_a_bit(setup, monkeypatch):
 
     m, lib, orc, p, ext = setup
     n0, n1 = 8190, 1000
-    d = torch.empty(n0 * n1 * 6, dtype=torch.float64, device="cuda:0")
+    guard = 1 << 16  # doubles on either side of the output: no tile may write outside it
+    whole = torch.empty(n0 * n1 * 6 + 2 * guard, dtype=torch.float64, device="cuda:0")
+    d = whole[guard:guard + n0 * n1 * 6]
 
     def run():
-        d.fill_(-7.0)
+        whole.fill_(-7.0)
         rep = rs.grid_eval(lib, "complete_analysis", p, None, n0, n1, ext, device=0,
                            out_device_ptr=d.data_ptr())  # fmt: skip
         assert rep["launches"] <= 3
-        return d.cpu().numpy().view(np.uint64).copy()
+        assert bool((whole[:guard] == -7.0).all()) and bool((whole[-guard:] == -7.0).all())
+        got = d.cpu().numpy()
+        assert not (got == -7.0).any()  # every record written
+        return got.view(np.uint64).copy()
 
     monkeypatch.setenv("INFLATOX_RPT_TAIL", "0")
     uniform = run()
