@@ -431,13 +431,19 @@ def main():
         fl = torch.empty(1 << 28, dtype=torch.uint8, device="cuda") if pts * c_per * 8 <= (1 << 28) else None
         c_ss = np.array(c_ext, dtype=np.float64)
         t_all = t_grid = 0.0
-        for i in range(warmup + steps):
+
+        def one_step():
             if fl is not None:
                 fl.fill_(1)
                 torch.cuda.synchronize()
-            r = rs.grid_eval(c_lib, c_op, c_p, None, c_n0, c_n1, c_ss, device=local,
-                             out_device_ptr=buf.data_ptr())  # fmt: skip
-            if i >= warmup:
+            return rs.grid_eval(c_lib, c_op, c_p, None, c_n0, c_n1, c_ss, device=local,
+                                out_device_ptr=buf.data_ptr())  # fmt: skip
+
+        for _ in range(warmup):
+            one_step()
+        with ClockSampler(local) as c_clocks:
+            for _ in range(steps):
+                r = one_step()
                 t_all += r["kernel_ms"]
                 t_grid += r["grid_ms"]
         del buf, fl
@@ -448,6 +454,7 @@ def main():
             "workload": config_dict(cfg, c_model, c_op, c_n0, c_n1, c_S, 1)["workload"],
             "value": pts * steps / (t_all / 1e3), "unit": "points/s", "steps": steps,
             "ms_per_step": t_all / steps, "dominant_kernel_ms_per_step": t_grid / steps,
+            "clocks": c_clocks.summary(),
             "roofline": {"bound": "fp64", "kernel": f"inflx_grid_{c_op}", "achieved": tf,
                          "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
                          "flops_per_point": c_F, "traffic": traffic_db.get(cfg),
@@ -461,6 +468,11 @@ def main():
         configs = {}
         for cfg in sorted(CONFIGS):
             if cfg != a.config:
+                # each line is an independent measurement: a second of idle lets the board's power
+                # averaging recover from the previous config (C5 streams 7 TB/s and leaves the
+                # next configs under sw_power_cap at 1770-1920 MHz otherwise); each line carries
+                # its own `clocks`
+                time.sleep(1.0)
                 configs[cfg] = device_only(cfg, max(3, min(a.steps, 10)), 3)
 
     # ---- N > 1: the one facade call a user makes, ONE process driving all N GPUs (rank 0) ---------
