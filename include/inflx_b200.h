@@ -167,7 +167,7 @@ typedef struct {
                              host output [n_vectors][4][rows][n1], device-resident output
                              [4][n_vectors][rows][n1] */
   int out_is_device;      /* 1: `out` is device memory on `device` and stays there (no copy);
-                             at most 65535 * (rows per CTA) rows per call */
+                             a sweep (n_vectors > 1) at most 65535 * (rows per CTA) rows per call */
   int device;             /* ordinal for out_is_device / single-device host calls; -1: shard
                              over the handle's devices */
   void *stream;           /* CUstream to launch on when out_is_device (NULL: internal stream).

@@ -516,9 +516,11 @@ static inflx_status run_shard(inflx_lib* lib, const inflx_grid_request& rq, cons
     rows_chunk = std::max<uint64_t>(RPT, target / (n1 * opb));
     rows_chunk = std::min<uint64_t>(rows_chunk - rows_chunk % RPT, rows_total);
   }
-  if (to_device && rows_total > 65535ull * RPT)
-    // one launch covers the rows of a device-resident request (gridDim.y <= 65535 row tiles)
-    return fail(INFLX_ERR_SHAPE, fmt("a device-resident output is limited to %llu rows per call "
+  // gridDim.y holds 65535 row tiles: taller shards take several launches.  A device-resident
+  // SWEEP cannot be cut by rows (its layout [vector][row][col] is indexed with the launch's row
+  // count), a single grid can: the launches write consecutive row blocks of the caller's buffer.
+  if (to_device && S > 1 && rows_total > 65535ull * RPT)
+    return fail(INFLX_ERR_SHAPE, fmt("a device-resident sweep is limited to %llu rows per call "
                                      "(%llu requested): split the request by rows",
                                      (unsigned long long)(65535ull * RPT),
                                      (unsigned long long)rows_total));
@@ -646,6 +648,7 @@ static inflx_status run_shard(inflx_lib* lib, const inflx_grid_request& rq, cons
       if (to_device) {
         // user buffer layout [S][rows_total][n1][k] (hesse: [4] outermost over the whole request)
         outp = (CUdeviceptr)rq.out + (hesse ? s0 * rows_total * n1 * 8 : s0 * rows_total * n1 * opb);
+        outp += (r0 - sh.rb) * n1 * (hesse ? 8 : opb);  // row block of a tall single grid (S == 1)
         if (hesse) comp_stride = S * rows_total * n1;
       } else {
         outp = dev->d_out[slot].ptr;

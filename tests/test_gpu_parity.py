@@ -320,6 +320,27 @@ def test_edge_shapes():
     rs.complete_analysis_on_trajectory(lib, p, np.zeros((0, 2)), out, False, 1)
 
 
+@pytest.mark.parametrize("shape", [(3, 9_000_001), (2_100_001, 5)])
+def test_extreme_aspect_ratios(shape):
+    """Launch-grid limits: 70 313 column tiles in gridDim.x; 2.1 M rows = more row tiles than
+    gridDim.y holds, so the engine must split the shard into several launches - device-resident
+    (one request) and through the chunked host path.  Ragged in both directions."""
+    import torch
+
+    n0, n1 = shape
+    lib = rs.open_inflx_dylib(cases.artifact("doc").shared_object_path, False)
+    lib.set_devices([0])
+    orc, p, ext = oracle.Oracle("doc"), cases.params("doc"), cases.EXTENT["doc"]
+    ref = orc.consistency_only(p, n0, n1, ext)
+    out = np.full((n0, n1), -7.0)
+    rs.consistency_only(lib, p, out, ss_of(ext), False, 0)
+    check("doc", out, ref, what=f"{n0}x{n1} host")
+    d = torch.full((n0 * n1,), -7.0, dtype=torch.float64, device="cuda:0")
+    rs.grid_eval(lib, "consistency_only", p, None, n0, n1, ext, device=0, out_device_ptr=d.data_ptr())
+    dev = d.cpu().numpy().reshape(n0, n1)
+    assert np.array_equal(dev.view(np.uint64), out.view(np.uint64))
+
+
 def test_full_size_rows_of_baseline_grids():
     """At BASELINE.json's full sizes the oracle cannot sweep the grid in seconds, but any ROW of
     the full grid can be checked: coordinates come from global indices, so rows evaluated as
