@@ -582,3 +582,158 @@ INFLX_GL_FN double inflx_gl_cos(double x) {
   }
   return INFLX_GL_DIV(x, x);
 }
+
+// ---- atan, tan --------------------------------------------------------------------------------------
+// The reference's epilogue (src/anguelova.rs:130-134) takes delta = atan(|V_wv / V_vv|) and
+// eta = omega * tan(delta) - 3 through Rust's f64::atan / f64::tan, i.e. the platform libm.  glibc
+// 2.39's atan and tan are IBM's "accurate mathematical library" routines (sysdeps/ieee754/dbl-64/
+// s_atan.c, s_tan.c) with the multi-precision fall-backs removed: table look-up (uatan.tbl: 241 x 7,
+// utan.tbl: 186 x 4; extracted into inflx_glibc_tables.cuh) + short polynomials + double-double
+// corrections.  Restated from the FMA ifunc variants of the shipped binary (__atan_fma, __tan_fma),
+// contraction included.  The grid kernels call them in libm flavour "glibc-all" only: the default
+// epilogue uses inflx_atan_tan (inflx_device.cuh; <= 1 ulp, half the instructions, no gathers).
+#define INFLX_GL_HAVE_ATAN_TAN 1
+
+INFLX_GL_INL double inflx_gl_copysign(double mag, double sgn) {
+  return INFLX_GL_FROM_BITS((INFLX_GL_BITS(mag) & 0x7fffffffffffffffull) |
+                            (INFLX_GL_BITS(sgn) & 0x8000000000000000ull));
+}
+
+INFLX_GL_FN double inflx_gl_atan(double x) {
+  const double d3 = -0x1.5555555555555p-2, d5 = 0x1.99999999997fdp-3, d7 = -0x1.24924923f7603p-3;
+  const double d9 = 0x1.c71c6e5129a3bp-4, d11 = -0x1.7458022b13c25p-4, d13 = 0x1.375f08b31cbcep-4;
+  const double hpi = 0x1.921fb54442d18p+0, hpi1 = 0x1.1a62633145c07p-54, two52 = 0x1p+52;
+  const inflx_gl_u64 bits = INFLX_GL_BITS(x);
+  if (((bits >> 52) & 0x7ff) == 0x7ff && (bits & 0x000fffffffffffffull)) return INFLX_GL_ADD(x, x);
+  const double u = fabs(x);
+  if (u < 1.0) {
+    if (u < 0.0625) {
+      if (u < 0x1.bb67ap-27) return x;
+      const double v = INFLX_GL_MUL(x, x);
+      double t = INFLX_GL_FMA(v, d13, d11);
+      t = INFLX_GL_FMA(v, t, d9);
+      t = INFLX_GL_FMA(v, t, d7);
+      t = INFLX_GL_FMA(v, t, d5);
+      t = INFLX_GL_FMA(v, t, d3);
+      return INFLX_GL_FMA(INFLX_GL_MUL(x, v), t, x);
+    }
+    const int i = (int)INFLX_GL_SUB(INFLX_GL_FMA(u, 256.0, two52), two52) - 16;
+    const double* c = inflx_gl_atan_cij + 7 * i;
+    const double z = INFLX_GL_SUB(u, c[0]);
+    double yy = INFLX_GL_FMA(z, c[6], c[5]);
+    yy = INFLX_GL_FMA(z, yy, c[4]);
+    yy = INFLX_GL_FMA(z, yy, c[3]);
+    yy = INFLX_GL_FMA(z, yy, c[2]);
+    return inflx_gl_copysign(INFLX_GL_FMA(yy, z, c[1]), x);
+  }
+  if (u < 16.0) {  // atan(u) = pi/2 - atan(1/u), 1/u to double-double
+    const double w = INFLX_GL_DIV(1.0, u);
+    const double t1 = INFLX_GL_MUL(w, u);
+    const double t2 = INFLX_GL_FMA(u, w, -t1);
+    const double r = INFLX_GL_SUB(INFLX_GL_SUB(1.0, t1), t2);
+    const int i = (int)INFLX_GL_SUB(INFLX_GL_FMA(w, 256.0, two52), two52) - 16;
+    const double* c = inflx_gl_atan_cij + 7 * i;
+    const double z = INFLX_GL_FMA(r, w, INFLX_GL_SUB(w, c[0]));
+    double yy = INFLX_GL_FMA(z, c[6], c[5]);
+    yy = INFLX_GL_FMA(z, yy, c[4]);
+    yy = INFLX_GL_FMA(z, yy, c[3]);
+    yy = INFLX_GL_FMA(z, yy, c[2]);
+    yy = INFLX_GL_FMA(-yy, z, hpi1);
+    return inflx_gl_copysign(INFLX_GL_ADD(INFLX_GL_SUB(hpi, c[1]), yy), x);
+  }
+  if (u < 0x1.49ff2p+52) {
+    const double w = INFLX_GL_DIV(1.0, u);
+    const double t1 = INFLX_GL_MUL(w, u);
+    const double t3 = INFLX_GL_SUB(hpi, w);
+    const double v = INFLX_GL_MUL(w, w);
+    double p = INFLX_GL_FMA(v, d13, d11);
+    p = INFLX_GL_FMA(v, p, d9);
+    p = INFLX_GL_FMA(v, p, d7);
+    p = INFLX_GL_FMA(v, p, d5);
+    p = INFLX_GL_FMA(v, p, d3);
+    const double cor = INFLX_GL_ADD(INFLX_GL_SUB(INFLX_GL_SUB(hpi, t3), w), hpi1);
+    const double t2 = INFLX_GL_FMA(u, w, -t1);
+    const double r = INFLX_GL_SUB(INFLX_GL_SUB(1.0, t1), t2);
+    const double s = INFLX_GL_FMA(-r, w, cor);
+    const double yy = INFLX_GL_FMA(-INFLX_GL_MUL(w, v), p, s);
+    return inflx_gl_copysign(INFLX_GL_ADD(t3, yy), x);
+  }
+  return x > 0.0 ? hpi : -hpi;
+}
+
+// tan for |x| <= 25 (the epilogue's argument is an atan: 0 <= x <= pi/2, or NaN).  Larger finite
+// arguments - s_tan.c's 25 < |x| <= 1e8 and __branred ranges, unreachable from the path - are NOT
+// restated and return NaN.
+INFLX_GL_FN double inflx_gl_tan(double x) {
+  const double d3 = 0x1.5555555555555p-2, d5 = 0x1.11111111107c6p-3, d7 = 0x1.ba1ba1cdb8745p-5;
+  const double d9 = 0x1.664ed49cfc666p-6, d11 = 0x1.2385a3cf2e4eap-7;
+  const double e0 = 0x1.5555555554dbdp-2, e1 = 0x1.11112e0a6b45fp-3, mfftnhf = -15.5;
+  const inflx_gl_u64 bits = INFLX_GL_BITS(x);
+  if (((bits >> 52) & 0x7ff) == 0x7ff) return INFLX_GL_SUB(x, x);  // inf, NaN
+  const double w = (x < 0.0) ? -x : x;
+  if (w <= 0x1.b096cp-27) return x;
+  if (w <= 0x1.f212dp-5) {
+    const double x2 = INFLX_GL_MUL(x, x);
+    double t = INFLX_GL_FMA(x2, d11, d9);
+    t = INFLX_GL_FMA(x2, t, d7);
+    t = INFLX_GL_FMA(x2, t, d5);
+    t = INFLX_GL_FMA(x2, t, d3);
+    return INFLX_GL_FMA(INFLX_GL_MUL(x, x2), t, x);
+  }
+  if (w <= 0x1.92f1ap-1) {
+    const int i = (int)INFLX_GL_FMA(w, 256.0, mfftnhf);
+    const double* g = inflx_gl_tan_xfg + 4 * i;
+    const double z = INFLX_GL_SUB(w, g[0]);
+    const double z2 = INFLX_GL_MUL(z, z);
+    const double pz = INFLX_GL_FMA(INFLX_GL_MUL(z, z2), INFLX_GL_FMA(z2, e1, e0), z);
+    const double fi = g[1], gi = g[2];
+    const double t2 = INFLX_GL_DIV(INFLX_GL_MUL(INFLX_GL_ADD(fi, gi), pz), INFLX_GL_SUB(gi, pz));
+    return INFLX_GL_MUL(INFLX_GL_ADD(t2, fi), (x < 0.0) ? -1.0 : 1.0);
+  }
+  if (!(w <= 25.0)) return INFLX_GL_NAN;  // not restated (see above)
+  // 0.787 < |x| <= 25: x = n pi/2 + (a + da)
+  const double hpinv = 0x1.45f306dc9c883p-1, toint = 0x1.8p+52;
+  const double mp1 = 0x1.921fb58p+0, mp2 = -0x1.dde973cp-27, mp3 = -0x1.cb3b399d747f2p-55;
+  const double t = INFLX_GL_FMA(x, hpinv, toint);
+  const double xn = INFLX_GL_SUB(t, toint);
+  const int n = (int)(INFLX_GL_BITS(t) & 1);
+  const double t1 = INFLX_GL_FMA(-xn, mp2, INFLX_GL_FMA(-xn, mp1, x));
+  const double a = INFLX_GL_FMA(-xn, mp3, t1);
+  const double da = INFLX_GL_FMA(-xn, mp3, INFLX_GL_SUB(t1, a));
+  double ya = a, yya = da, sy = 1.0;
+  if (0.0 > a) {
+    ya = -a;
+    yya = -da;
+    sy = -1.0;
+  }
+  if (!(0x1.f212dp-5 < ya)) {  // |a| <= 0.0608: polynomial, and for odd n -cot through a dd division
+    const double a2 = INFLX_GL_MUL(a, a);
+    double p = INFLX_GL_FMA(a2, d11, d9);
+    p = INFLX_GL_FMA(a2, p, d7);
+    p = INFLX_GL_FMA(a2, p, d5);
+    p = INFLX_GL_FMA(a2, p, d3);
+    const double t2 = INFLX_GL_FMA(INFLX_GL_MUL(a, a2), p, da);
+    const double b = INFLX_GL_ADD(a, t2);
+    if (!n) return b;
+    const double db = (fabs(a) > fabs(t2)) ? INFLX_GL_ADD(INFLX_GL_SUB(a, b), t2)
+                                           : INFLX_GL_ADD(INFLX_GL_SUB(t2, b), a);
+    const double c = INFLX_GL_DIV(1.0, b);
+    const double ph = INFLX_GL_MUL(c, b);
+    const double pl = INFLX_GL_FMA(c, b, -ph);
+    double r = INFLX_GL_ADD(INFLX_GL_SUB(INFLX_GL_SUB(1.0, ph), pl), 0.0);
+    r = INFLX_GL_FMA(-db, c, r);
+    const double cc = INFLX_GL_DIV(r, b);
+    const double zh = INFLX_GL_ADD(c, cc);
+    const double zl = INFLX_GL_ADD(INFLX_GL_SUB(c, zh), cc);
+    return -INFLX_GL_ADD(zl, zh);
+  }
+  const int i = (int)INFLX_GL_FMA(ya, 256.0, mfftnhf);
+  const double* g = inflx_gl_tan_xfg + 4 * i;
+  const double z = INFLX_GL_ADD(INFLX_GL_SUB(ya, g[0]), yya);
+  const double z2 = INFLX_GL_MUL(z, z);
+  const double pz = INFLX_GL_FMA(INFLX_GL_MUL(z, z2), INFLX_GL_FMA(z2, e1, e0), z);
+  const double fi = g[1], gi = g[2];
+  const double s = INFLX_GL_MUL(INFLX_GL_ADD(fi, gi), pz);
+  if (n) return INFLX_GL_MUL(INFLX_GL_SUB(gi, INFLX_GL_DIV(s, INFLX_GL_ADD(pz, fi))), -sy);
+  return INFLX_GL_MUL(INFLX_GL_ADD(INFLX_GL_DIV(s, INFLX_GL_SUB(gi, pz)), fi), sy);
+}

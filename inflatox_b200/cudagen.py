@@ -537,7 +537,10 @@ class GroupProgram:
             with open(os.path.join(_CSRC, "inflx_glibcmath.cuh")) as fh:
                 device_header += "\n" + fh.read().replace('#include "inflx_glibc_tables.cuh"', tables)
         npf, nrf = len(self.p_frontier), self.n_row_slots
-        src = [f"#define INFLX_GROUP_MIN_BLOCKS {self.min_blocks}\n", device_header]
+        src = [f"#define INFLX_GROUP_MIN_BLOCKS {self.min_blocks}\n"]
+        if self.libm == "glibc-all":  # the epilogue's atan / tan are the reference host's too
+            src.append("#define INFLX_EXACT_ATAN_TAN 1\n")
+        src.append(device_header)
         src.append(f'\n// ===== generated: model "{model_name}", group "{self.group}" =====\n')
         src.append(f"#define INFLX_NP {self.n_params}\n#define INFLX_NPF {npf}\n")
         src.append(f"#define INFLX_NRF {nrf}\n#define INFLX_PC_CAP {PC_CAPACITY}\n")

@@ -46,9 +46,9 @@ static double arg_y(rng_t* r, int f) {
 
 int main(int argc, char** argv) {
   long n = argc > 1 ? atol(argv[1]) : 1000000;
-  long bad_pow = 0, bad_exp = 0, bad_log = 0, bad_sin = 0, bad_cos = 0, bad_tanh = 0, bad_expm1 = 0, bad_special = 0;
-  double worst[7][2] = {{0}};
-#pragma omp parallel for reduction(+ : bad_pow, bad_exp, bad_log, bad_sin, bad_cos, bad_tanh, bad_expm1) schedule(static)
+  long bad_pow = 0, bad_exp = 0, bad_log = 0, bad_sin = 0, bad_cos = 0, bad_tanh = 0, bad_expm1 = 0, bad_special = 0, bad_atan = 0, bad_tan = 0;
+  double worst[9][2] = {{0}};
+#pragma omp parallel for reduction(+ : bad_pow, bad_exp, bad_log, bad_sin, bad_cos, bad_tanh, bad_expm1, bad_atan, bad_tan) schedule(static)
   for (long i = 0; i < n; i++) {
     rng_t r = {0x1234567ull + 0x9e3779b97f4a7c15ull * (uint64_t)i};
     const int f = (int)(i % 7);
@@ -91,6 +91,27 @@ int main(int argc, char** argv) {
     if (!same(inflx_gl_expm1(xt), expm1(xt))) { bad_expm1++; worst[6][0] = xt; }
     if (!same(inflx_gl_expm1(xe), expm1(xe))) { bad_expm1++; worst[6][0] = xe; }
 #endif
+#ifdef INFLX_GL_HAVE_ATAN_TAN
+    double xa;
+    switch (i % 6) {
+      case 0: xa = exp(60 * (unif(&r) - 0.5)); break;                           /* every branch of atan */
+      case 1: xa = 20 * (unif(&r) - 0.5); break;
+      case 2: xa = ldexp(unif(&r) - 0.5, -(int)(40 * unif(&r))); break;
+      case 3: xa = (unif(&r) - 0.5) * 2.2; break;                               /* around the 1/16 and 1 seams */
+      case 4: xa = ldexp(1 + unif(&r), (int)(120 * (unif(&r) - 0.5))); break;
+      default: xa = anybits(&r);
+    }
+    if (!same(inflx_gl_atan(xa), atan(xa))) { bad_atan++; worst[7][0] = xa; }
+    double xq;
+    switch (i % 5) {
+      case 0: xq = M_PI_2 * unif(&r); break;                                    /* the epilogue's range */
+      case 1: xq = atan(exp(60 * (unif(&r) - 0.5))); break;                     /* tan(atan(y)), any y */
+      case 2: xq = 50 * (unif(&r) - 0.5); break;                                /* |x| <= 25 */
+      case 3: xq = ldexp(unif(&r) - 0.5, -(int)(40 * unif(&r))); break;
+      default: xq = (double)(long)(16 * unif(&r)) * M_PI_2 * (1 + (unif(&r) - 0.5) * ldexp(1.0, -(int)(50 * unif(&r))));
+    }
+    if (fabs(xq) <= 25.0 && !same(inflx_gl_tan(xq), tan(xq))) { bad_tan++; worst[8][0] = xq; }
+#endif
   }
   /* hand-picked irregular arguments: signs of zeros and infinities included */
   const double sp[][2] = {{0, 2}, {-1, 2}, {-8, 1.0 / 3}, {INFINITY, -1}, {NAN, 1}, {2, NAN}, {2, 0},
@@ -117,9 +138,28 @@ int main(int argc, char** argv) {
     bad_special += !same(inflx_gl_tanh(s1[i]), tanh(s1[i]));
     bad_special += !same(inflx_gl_expm1(s1[i]), expm1(s1[i]));
 #endif
+#ifdef INFLX_GL_HAVE_ATAN_TAN
+    bad_special += !same(inflx_gl_atan(s1[i]), atan(s1[i]));
+    bad_special += !same(inflx_gl_atan(-s1[i]), atan(-s1[i]));
+    if (!(fabs(s1[i]) > 25.0)) bad_special += !same(inflx_gl_tan(s1[i]), tan(s1[i]));
+#endif
   }
-  printf("n=%ld bad_pow=%ld bad_exp=%ld bad_log=%ld bad_sin=%ld bad_cos=%ld bad_tanh=%ld bad_expm1=%ld bad_special=%ld\n",
-         n, bad_pow, bad_exp, bad_log, bad_sin, bad_cos, bad_tanh, bad_expm1, bad_special);
+#ifdef INFLX_GL_HAVE_ATAN_TAN
+  const double s2[] = {0.0625, 1.0, 16.0, 0x1.49ff2p+52, 0x1.bb67ap-27, 0x1.b096cp-27, 0x1.f212dp-5,
+                       0x1.92f1ap-1, 25.0, M_PI_2, M_PI_4, 0x1.921fb54442d18p+0, 0x1.921fb54442d19p+0,
+                       0x1.921fb54442d17p+0, 3 * M_PI_2, 0.99999999999999989, 15.999999999999998};
+  for (unsigned i = 0; i < sizeof s2 / sizeof s2[0]; i++)
+    for (int sg = -1; sg <= 1; sg += 2)
+      for (int d = -2; d <= 2; d++) {
+        double v = s2[i];
+        for (int k = 0; k < (d < 0 ? -d : d); k++) v = nextafter(v, d < 0 ? 0.0 : INFINITY);
+        v *= sg;
+        bad_special += !same(inflx_gl_atan(v), atan(v));
+        if (fabs(v) <= 25.0) bad_special += !same(inflx_gl_tan(v), tan(v));
+      }
+#endif
+  printf("n=%ld bad_pow=%ld bad_exp=%ld bad_log=%ld bad_sin=%ld bad_cos=%ld bad_tanh=%ld bad_expm1=%ld bad_atan=%ld bad_tan=%ld bad_special=%ld\n",
+         n, bad_pow, bad_exp, bad_log, bad_sin, bad_cos, bad_tanh, bad_expm1, bad_atan, bad_tan, bad_special);
   if (bad_pow) printf("pow example: x=%a y=%a ours=%a libm=%a\n", worst[0][0], worst[0][1],
                       inflx_gl_pow(worst[0][0], worst[0][1]), pow(worst[0][0], worst[0][1]));
   if (bad_exp) printf("exp example: x=%a ours=%a libm=%a\n", worst[1][0], inflx_gl_exp(worst[1][0]), exp(worst[1][0]));
@@ -131,6 +171,10 @@ int main(int argc, char** argv) {
 #ifdef INFLX_GL_HAVE_TANH
   if (bad_expm1) printf("expm1 example: x=%a ours=%a libm=%a\n", worst[6][0], inflx_gl_expm1(worst[6][0]), expm1(worst[6][0]));
   if (bad_tanh) printf("tanh example: x=%a ours=%a libm=%a\n", worst[5][0], inflx_gl_tanh(worst[5][0]), tanh(worst[5][0]));
+#endif
+#ifdef INFLX_GL_HAVE_ATAN_TAN
+  if (bad_atan) printf("atan example: x=%a ours=%a libm=%a\n", worst[7][0], inflx_gl_atan(worst[7][0]), atan(worst[7][0]));
+  if (bad_tan) printf("tan example: x=%a ours=%a libm=%a\n", worst[8][0], inflx_gl_tan(worst[8][0]), tan(worst[8][0]));
 #endif
   return 0;
 }

@@ -68,9 +68,13 @@ def test_libm_flavours_of_the_hoisted_calls():
     assert "inflx_powi<" not in rows and "inflx_powh" not in rows  # no dd chain in a hoisted class
     src = cudagen.ModelProgram(unit, libm="cr").groups["cmp"].cuda_source("egno")
     assert "inflx_powi<3>(" in src and "inflx_powh<1>(" in src and "inflx_powh_neg<0>(" in src
-    assert "inflx_cr_pow(" in src and "inflx_gl_" not in src
+    assert "inflx_cr_pow(" in src and "inflx_gl_pow" not in src and "INFLX_EXACT_ATAN_TAN 1" not in src
     src = cudagen.ModelProgram(unit, libm="device").groups["cmp"].cuda_source("egno")
-    assert "inflx_cr_" not in src and "inflx_gl_" not in src and " pow(" in src
+    assert "inflx_cr_" not in src and "inflx_gl_pow" not in src and " pow(" in src
+    # "glibc-all": per-point powers and the epilogue's atan / tan through the restated glibc too
+    src = cudagen.ModelProgram(unit, libm="glibc-all").groups["cmp"].cuda_source("egno")
+    assert src.startswith("#define INFLX_GROUP_MIN_BLOCKS") and "#define INFLX_EXACT_ATAN_TAN 1" in src
+    assert "double inflx_gl_atan(double x) {" in src and "double inflx_gl_tan(double x) {" in src
     with pytest.raises(Exception, match="unknown libm flavour"):
         cudagen.ModelProgram(unit, libm="musl")
 

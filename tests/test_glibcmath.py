@@ -55,7 +55,8 @@ def test_every_result_has_the_bits_of_the_host_libm(checker):
     out = subprocess.run([checker, str(n)], capture_output=True, text=True, check=True).stdout
     c = {k: int(v) for k, v in re.findall(r"(\w+)=(\d+)", out.splitlines()[0])}
     assert c["n"] == n
-    for k in ("bad_pow", "bad_exp", "bad_log", "bad_sin", "bad_cos", "bad_tanh", "bad_expm1", "bad_special"):
+    for k in ("bad_pow", "bad_exp", "bad_log", "bad_sin", "bad_cos", "bad_tanh", "bad_expm1", "bad_atan", "bad_tan",
+              "bad_special"):
         assert c[k] == 0, out
 
 

@@ -267,9 +267,12 @@ def test_correctly_rounded_libm_matches_the_host_build(tmp_path, fmad):
 # ---------------------------------------------------------------------------------------------
 GL_SRC = r"""
 extern "C" __global__ void t_gl(const double* x, const double* y, double* p, double* l, double* e,
-                                double* s, double* c, double* t, double* m, int n) {
+                                double* s, double* c, double* t, double* m, double* a, double* q,
+                                int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  a[i] = inflx_gl_atan(x[i]);
+  q[i] = inflx_gl_tan(inflx_gl_atan(fabs(y[i])));  // the epilogue's composition: argument in [0, pi/2]
   p[i] = inflx_gl_pow(x[i], y[i]);
   l[i] = inflx_gl_log(x[i]);
   e[i] = inflx_gl_exp(y[i]);
@@ -282,8 +285,10 @@ extern "C" __global__ void t_gl(const double* x, const double* y, double* p, dou
 GL_HOST = r"""
 #include <math.h>
 void host_libm(const double* x, const double* y, double* p, double* l, double* e, double* s,
-               double* c, double* t, double* m, long n) {
+               double* c, double* t, double* m, double* a, double* q, long n) {
   for (long i = 0; i < n; i++) {
+    a[i] = atan(x[i]);
+    q[i] = tan(atan(fabs(y[i])));
     p[i] = pow(x[i], y[i]);
     l[i] = log(x[i]);
     e[i] = exp(y[i]);
@@ -324,8 +329,8 @@ def test_glibc_libm_on_the_device_has_the_bits_of_the_host_libm(tmp_path, fmad):
     y[2 * q:3 * q] = np.where(rng.random(q) < 0.5, rng.integers(1, 9, q) * 0.5, 4 * np.pi * rng.random(q))
     x[3 * q:], y[3 * q:] = _random_doubles(rng, n - 3 * q), _random_doubles(rng, n - 3 * q)[::-1]
     x, y = np.ascontiguousarray(x), np.ascontiguousarray(y)
-    outs_d = [np.zeros(n) for _ in range(7)]
-    outs_h = [np.zeros(n) for _ in range(7)]
+    outs_d = [np.zeros(n) for _ in range(9)]
+    outs_h = [np.zeros(n) for _ in range(9)]
     with open(os.path.join(csrc, "inflx_glibc_tables.cuh")) as fh:
         tables = fh.read()
     with open(os.path.join(csrc, "inflx_glibcmath.cuh")) as fh:
@@ -334,7 +339,8 @@ def test_glibc_libm_on_the_device_has_the_bits_of_the_host_libm(tmp_path, fmad):
     mod.launch("t_gl", n, [x, y], outs_d)
     dp = ctypes.POINTER(ctypes.c_double)
     host.host_libm(*[a.ctypes.data_as(dp) for a in [x, y] + outs_h], ctypes.c_long(n))
-    for name, d, h in zip(("pow", "log", "exp", "sin", "cos", "tanh", "expm1"), outs_d, outs_h):
+    names = ("pow", "log", "exp", "sin", "cos", "tanh", "expm1", "atan", "tan(atan)")
+    for name, d, h in zip(names, outs_d, outs_h):
         same = _same(d, h)
         bad = np.flatnonzero(~same)
         assert same.all(), (name, bad.size, x[bad[:3]], y[bad[:3]], d[bad[:3]], h[bad[:3]])

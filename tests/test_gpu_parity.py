@@ -55,30 +55,40 @@ def test_complete_analysis(setup):
         check(m, out[..., k], ref[..., k], what=name)
 
 
-@pytest.mark.parametrize("model", ["egno", "d5"])
-def test_flavour_glibc_all_is_bit_identical_outside_atan(model):
-    """`INFLATOX_LIBM=glibc-all` sends the per-point literal half-integer powers of EGNO and d5
-    through the restated glibc `pow` as well (default: correctly rounded dd chains, which differ
-    from glibc's in the last bit on ~1e-3 of the calls).  Every operation of the path is then the
-    reference's own - IEEE +,-,*,/,sqrt and glibc's libm - except the epilogue's atan / tan, so the
-    four planes that do not pass through them (consistency, eps_V, eps_H, omega) and the single-
-    plane ops must equal the oracle's BIT FOR BIT; delta and eta stay within 1e-10."""
+@pytest.mark.parametrize("model", cases.MODELS)
+def test_flavour_glibc_all_reproduces_every_bit_of_the_oracle(model):
+    """`INFLATOX_LIBM=glibc-all`: the per-point literal half-integer powers of EGNO and d5 go through
+    the restated glibc `pow` (default: correctly rounded dd chains, which differ from glibc's in
+    the last bit on ~1e-3 of the calls) and the epilogue's delta / tan(delta) through the restated
+    glibc `atan` / `tan`.  Every operation of the path is then the reference's own - IEEE
+    +,-,*,/,sqrt and glibc's libm - so all six planes, the single-plane ops and the on-trajectory
+    op must equal the oracle's BIT FOR BIT."""
     lib = rs.open_inflx_dylib(cases.artifact(model, libm="glibc-all").shared_object_path, False)
     lib.set_devices([0])
     orc, p, ext = oracle.Oracle(model), cases.params(model), cases.EXTENT[model]
+
+    def same(a, b):
+        return (a.view(np.uint64) == b.view(np.uint64)) | (np.isnan(a) & np.isnan(b)) | ((a == 0) & (b == 0))
+
     out = np.zeros((N0, N1, 6))
     rs.complete_analysis(lib, p, out, ss_of(ext), False, 0)
     ref = orc.complete_analysis(p, N0, N1, ext)
     for k, name in enumerate(["consistency", "eps_V", "eps_H", "eta", "delta", "omega"]):
-        check(model, out[..., k], ref[..., k], what=name)
-        if name not in ("eta", "delta"):
-            same = (out[..., k].view(np.uint64) == ref[..., k].view(np.uint64)) | (
-                np.isnan(out[..., k]) & np.isnan(ref[..., k]))
-            assert same.all(), f"{model} {name}: {int((~same).sum())} points differ in the last bits"
+        ok = same(out[..., k], ref[..., k])
+        assert ok.all(), f"{model} {name}: {int((~ok).sum())} points differ in the last bits"
     one = np.zeros((N0, N1))
     rs.consistency_only(lib, p, one, ss_of(ext), False, 0)
-    ref1 = orc.consistency_only(p, N0, N1, ext)
-    assert ((one.view(np.uint64) == ref1.view(np.uint64)) | (np.isnan(one) & np.isnan(ref1))).all()
+    assert same(one, orc.consistency_only(p, N0, N1, ext)).all()
+    if model in ("angular", "egno", "d5"):
+        xs = np.ascontiguousarray(cases.trajectory(model)[:2000])
+    else:
+        rng = np.random.default_rng(11)
+        xs = np.ascontiguousarray(np.stack([rng.uniform(ext[0], ext[1], 2000),
+                                            rng.uniform(ext[2], ext[3], 2000)], axis=1))
+    traj = np.zeros((xs.shape[0], 6))
+    rs.complete_analysis_on_trajectory(lib, p, xs, traj, False, 0)
+    ok = same(traj, orc.complete_analysis_on_trajectory(p, xs))
+    assert ok.all(), f"{model} on trajectory: {int((~ok).sum())} values differ"
 
 
 @pytest.mark.parametrize(

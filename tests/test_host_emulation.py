@@ -107,6 +107,22 @@ def test_generated_kernels_reproduce_the_oracle(model, workdir):
         assert same.mean() >= 0.999, (model, k, float(same.mean()))
 
 
+@pytest.mark.parametrize("model", cases.MODELS)
+def test_flavour_glibc_all_reproduces_every_bit_of_the_oracle(model, workdir):
+    """libm="glibc-all": per-point half-integer powers through the restated glibc pow AND the
+    epilogue's delta / tan(delta) through the restated glibc atan / tan.  No operation of the path
+    then differs from the reference's: all six planes of every model equal the oracle's bit for bit
+    (NaNs at the same places)."""
+    prog = cudagen.ModelProgram(cexpr.parse_c_unit(oracle.golden_c_text(model)), libm="glibc-all")
+    emu = Emulated(prog, model + "_glall", "cmp", "complete_analysis", workdir)
+    p, ext, n0, n1 = cases.params(model), cases.EXTENT[model], 237, 331
+    got = emu.grid(p, n0, n1, ext)
+    ref = oracle.Oracle(model).complete_analysis(p, n0, n1, ext)
+    for k, name in enumerate(["consistency", "eps_V", "eps_H", "eta", "delta", "omega"]):
+        same = _same_bits(got[..., k], ref[..., k])
+        assert same.all(), (model, name, int((~same).sum()))
+
+
 @pytest.mark.parametrize("model", ["angular", "egno"])
 def test_correctly_rounded_flavour_differs_from_the_oracle_only_where_glibc_misrounds(model, workdir):
     """The round-1 flavour (libm="cr") stays available: every finite point within 1e-10 of the
