@@ -1,5 +1,5 @@
 // inflx_glibcmath.cuh - the libm the REFERENCE runs, restated for the device: bit-identical pow / exp /
-// log (and, further down, sin / cos / tanh) to glibc 2.39's x86_64 FMA builds.
+// log (and, further down, sin / cos / tanh / atan / tan) to glibc 2.39's x86_64 FMA builds.
 //
 // Why: the reference's arithmetic is "C compiler + platform libm" (reference
 // python/inflatox/compiler.py:299-310 links the generated model with -lm; SURVEY.md 8c "third-party

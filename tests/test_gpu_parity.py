@@ -6,8 +6,9 @@ finite point - asserted here for EVERY finite point of every model, plane and en
 (pow, log, exp, sin, cos, tanh per parameter vector / row / column) return the bits of the
 reference host's glibc (csrc/inflx_glibcmath.cuh): round 1's residue (EGNO 99.0-99.7 %, angular
 99.87-100 % within 1e-10) was glibc's own misrounding of a row-level pow, amplified by the
-models' conditioning.  What may still differ in the last bits: the epilogue's atan / tan
-(delta, eta) and per-point literal half-integer powers (correctly rounded dd chains).
+models' conditioning.  What may still differ in the last bits in the default build: the epilogue's
+atan / tan (delta, eta) and per-point literal half-integer powers (correctly rounded dd chains);
+libm flavour "glibc-all" removes both, and every output bit is then the oracle's.
 """
 import ctypes
 import math

@@ -66,13 +66,15 @@ def main():
     ap.add_argument("--fmad", action="store_true")
     ap.add_argument("--cr", action="store_true",
                     help="also compare with the oracle variant whose libm is correctly rounded")
+    ap.add_argument("--libm", default=None, help="libm flavour of the artefacts (cudagen.LIBM_FLAVOURS)")
+    ap.add_argument("--no-timing", action="store_true")
     ap.add_argument("--models", nargs="*", default=list(cases.MODELS))
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
-    report = {"n": a.n, "fmad": a.fmad, "models": {}}
+    report = {"n": a.n, "fmad": a.fmad, "libm": a.libm or "glibc (default)", "models": {}}
     for m in a.models:
         t0 = time.time()
-        art = cases.artifact(m, a.fmad)
+        art = cases.artifact(m, a.fmad, a.libm)
         lib = rs.open_inflx_dylib(art.shared_object_path, False)
         t_compile = time.time() - t0
         p, ext = cases.params(m), cases.EXTENT[m]
@@ -106,15 +108,16 @@ def main():
             }
         # timing: device-resident kernel-only via report, host end-to-end
         big = 4096
-        outb = rs.pinned_empty((big, big, 6))
-        for _ in range(2):
-            rep = rs.grid_eval(lib, "complete_analysis", p, outb, big, big, ss.reshape(4))
-        entry["timing_4096"] = {
-            "kernel_ms_incl_copies": rep["kernel_ms"],
-            "total_ms": rep["total_ms"],
-            "e2e_points_per_s": big * big / (rep["total_ms"] / 1e3),
-            "launches": rep["launches"],
-        }
+        if not a.no_timing:
+            outb = rs.pinned_empty((big, big, 6))
+            for _ in range(2):
+                rep = rs.grid_eval(lib, "complete_analysis", p, outb, big, big, ss.reshape(4))
+            entry["timing_4096"] = {
+                "kernel_ms_incl_copies": rep["kernel_ms"],
+                "total_ms": rep["total_ms"],
+                "e2e_points_per_s": big * big / (rep["total_ms"] / 1e3),
+                "launches": rep["launches"],
+            }
         report["models"][m] = entry
         print(m, json.dumps(entry, indent=None)[:1500], flush=True)
     if a.out:
