@@ -196,6 +196,45 @@ INFLX_GL_INL int inflx_gl_checkint(inflx_gl_u64 iy) {
   return 2;
 }
 
+// log_inline(ix) = hi + lo and its product with y as ehi + elo: the middle of pow, shared by the
+// out-of-line routine and the inlined per-point fast path.
+INFLX_GL_INL void inflx_gl_pow_log_mul(inflx_gl_u64 ix, double y, double* ehi_out, double* elo_out) {
+  // ---- log_inline: log(x) = k ln2 + log(c) + log1p(z/c - 1) as hi + lo ----
+  const inflx_gl_u64 tmp = ix - 0x3fe6955500000000ull;
+  const int i = (int)((tmp >> 45) & 127);
+  const int k = (int)((inflx_gl_i64)tmp >> 52);
+  const double z = INFLX_GL_FROM_BITS(ix - (tmp & (0xfffull << 52)));
+  const double kd = (double)k;
+  const double invc = inflx_gl_pow_log_tab[3 * i], logc = inflx_gl_pow_log_tab[3 * i + 1];
+  const double logctail = inflx_gl_pow_log_tab[3 * i + 2];
+  const double* A = inflx_gl_pow_poly;
+  const double t1 = INFLX_GL_FMA(kd, INFLX_GL_LN2HI, logc);
+  const double lo1 = INFLX_GL_FMA(kd, INFLX_GL_LN2LO, logctail);
+  const double r = INFLX_GL_FMA(z, invc, -1.0);
+  const double ar = INFLX_GL_MUL(r, A[0]);
+  const double p12 = INFLX_GL_FMA(A[2], r, A[1]);
+  const double p34 = INFLX_GL_FMA(A[4], r, A[3]);
+  const double t2 = INFLX_GL_ADD(r, t1);
+  const double lo2 = INFLX_GL_ADD(INFLX_GL_SUB(t1, t2), r);
+  const double ar2 = INFLX_GL_MUL(r, ar);
+  const double ar3 = INFLX_GL_MUL(r, ar2);
+  const double lo3 = INFLX_GL_FMA(ar, r, -ar2);
+  const double lhi = INFLX_GL_ADD(t2, ar2);
+  double p = INFLX_GL_FMA(r, A[6], A[5]);
+  p = INFLX_GL_FMA(p, ar2, p34);
+  const double lo4 = INFLX_GL_ADD(INFLX_GL_SUB(t2, lhi), ar2);
+  p = INFLX_GL_FMA(ar2, p, p12);
+  double llo = INFLX_GL_ADD(lo1, lo2);
+  llo = INFLX_GL_ADD(llo, lo3);
+  llo = INFLX_GL_ADD(llo, lo4);
+  llo = INFLX_GL_FMA(ar3, p, llo);
+  const double hi = INFLX_GL_ADD(lhi, llo);
+  const double lo = INFLX_GL_ADD(INFLX_GL_SUB(lhi, hi), llo);
+  // ---- y * log(x) as ehi + elo ----
+  *ehi_out = INFLX_GL_MUL(y, hi);
+  *elo_out = INFLX_GL_FMA(y, lo, INFLX_GL_FMA(hi, y, -*ehi_out));
+}
+
 INFLX_GL_FN double inflx_gl_pow(double x, double y) {
   inflx_gl_u64 sign_bias = 0;
   inflx_gl_u64 ix = INFLX_GL_BITS(x);
@@ -237,40 +276,8 @@ INFLX_GL_FN double inflx_gl_pow(double x, double y) {
       ix -= 52ull << 52;
     }
   }
-  // ---- log_inline: log(x) = k ln2 + log(c) + log1p(z/c - 1) as hi + lo ----
-  const inflx_gl_u64 tmp = ix - 0x3fe6955500000000ull;
-  const int i = (int)((tmp >> 45) & 127);
-  const int k = (int)((inflx_gl_i64)tmp >> 52);
-  const double z = INFLX_GL_FROM_BITS(ix - (tmp & (0xfffull << 52)));
-  const double kd = (double)k;
-  const double invc = inflx_gl_pow_log_tab[3 * i], logc = inflx_gl_pow_log_tab[3 * i + 1];
-  const double logctail = inflx_gl_pow_log_tab[3 * i + 2];
-  const double* A = inflx_gl_pow_poly;
-  const double t1 = INFLX_GL_FMA(kd, INFLX_GL_LN2HI, logc);
-  const double lo1 = INFLX_GL_FMA(kd, INFLX_GL_LN2LO, logctail);
-  const double r = INFLX_GL_FMA(z, invc, -1.0);
-  const double ar = INFLX_GL_MUL(r, A[0]);
-  const double p12 = INFLX_GL_FMA(A[2], r, A[1]);
-  const double p34 = INFLX_GL_FMA(A[4], r, A[3]);
-  const double t2 = INFLX_GL_ADD(r, t1);
-  const double lo2 = INFLX_GL_ADD(INFLX_GL_SUB(t1, t2), r);
-  const double ar2 = INFLX_GL_MUL(r, ar);
-  const double ar3 = INFLX_GL_MUL(r, ar2);
-  const double lo3 = INFLX_GL_FMA(ar, r, -ar2);
-  const double lhi = INFLX_GL_ADD(t2, ar2);
-  double p = INFLX_GL_FMA(r, A[6], A[5]);
-  p = INFLX_GL_FMA(p, ar2, p34);
-  const double lo4 = INFLX_GL_ADD(INFLX_GL_SUB(t2, lhi), ar2);
-  p = INFLX_GL_FMA(ar2, p, p12);
-  double llo = INFLX_GL_ADD(lo1, lo2);
-  llo = INFLX_GL_ADD(llo, lo3);
-  llo = INFLX_GL_ADD(llo, lo4);
-  llo = INFLX_GL_FMA(ar3, p, llo);
-  const double hi = INFLX_GL_ADD(lhi, llo);
-  const double lo = INFLX_GL_ADD(INFLX_GL_SUB(lhi, hi), llo);
-  // ---- y * log(x) as ehi + elo ----
-  const double ehi = INFLX_GL_MUL(y, hi);
-  const double elo = INFLX_GL_FMA(y, lo, INFLX_GL_FMA(hi, y, -ehi));
+  double ehi, elo;
+  inflx_gl_pow_log_mul(ix, y, &ehi, &elo);
   // ---- exp_inline(ehi, elo, sign_bias) ----
   const unsigned abstop = (unsigned)(INFLX_GL_BITS(ehi) >> 52) & 0x7ff;
   int special = 0;
@@ -286,6 +293,22 @@ INFLX_GL_FN double inflx_gl_pow(double x, double y) {
     special = 1;
   }
   return inflx_gl_exp_core(ehi, elo, 1, sign_bias, special);
+}
+
+// Per grid point (libm flavour "glibc-all"): the main path of pow inlined - x a positive normal,
+// |y| neither huge nor tiny, exp(y log x) far from over- and underflow - everything else through
+// the out-of-line routine.  Same operations, so the same bits.
+INFLX_GL_INL double inflx_gl_pow_m(double x, double y) {
+  const inflx_gl_u64 ix = INFLX_GL_BITS(x);
+  const unsigned topx = (unsigned)(ix >> 52);
+  const unsigned topy = (unsigned)(INFLX_GL_BITS(y) >> 52);
+  if (topx - 0x001u >= 0x7ffu - 0x001u || (topy & 0x7ffu) - 0x3beu >= 0x43eu - 0x3beu)
+    return inflx_gl_pow(x, y);
+  double ehi, elo;
+  inflx_gl_pow_log_mul(ix, y, &ehi, &elo);
+  const unsigned abstop = (unsigned)(INFLX_GL_BITS(ehi) >> 52) & 0x7ff;
+  if (abstop - 0x3c9u >= 0x3fu) return inflx_gl_pow(x, y);
+  return inflx_gl_exp_core(ehi, elo, 1, 0, 0);
 }
 
 // ---- expm1, tanh ------------------------------------------------------------------------------------

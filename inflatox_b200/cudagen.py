@@ -466,6 +466,8 @@ class GroupProgram:
             if hoisted is not None:
                 # evaluated once per parameter vector / grid row / grid column: afford the
                 # reference's own libm (or the correctly rounded one), see LIBM_FLAVOURS
+                if name == "pow" and hoisted == "inflx_gl_" and self.klass(i) == "M":
+                    name = "pow_m"  # per point: main path inlined, the rest out of line
                 return f"{hoisted}{name}({', '.join(args)})"
             if name == "pow" and d.is_const(n[3]):
                 e = float(d.cval(n[3]))

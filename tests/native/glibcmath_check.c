@@ -54,6 +54,7 @@ int main(int argc, char** argv) {
     const int f = (int)(i % 7);
     const double x = arg_x(&r, f), y = arg_y(&r, f);
     if (!same(inflx_gl_pow(x, y), pow(x, y))) { bad_pow++; worst[0][0] = x; worst[0][1] = y; }
+    if (!same(inflx_gl_pow_m(x, y), pow(x, y))) { bad_pow++; worst[0][0] = x; worst[0][1] = y; }  /* per-point variant */
     double xe;
     switch (i % 5) {
       case 0: xe = 1500 * (unif(&r) - 0.5); break;

@@ -104,7 +104,7 @@ def test_hoisted_libm_calls_use_the_reference_libm_and_expensive_columns_get_a_p
                 if n[0] == "f" and n[1] in cudagen.GL_FUNCTIONS:
                     if gp.klass(i) == "M":
                         # the only per-point calls of the test models: pow(., 3/2), pow(., -1/2)
-                        # (EGNO, d5) - dd chains by default, inflx_gl_pow in flavour "glibc-all"
+                        # (EGNO, d5) - dd chains by default, inflx_gl_pow_m in flavour "glibc-all"
                         assert n[1] == "pow" and gp.dag.cval(n[3]) in (1.5, -0.5), (m, g, n)
                         assert gp._hoisted_libm(i) is None
                     else:
@@ -115,7 +115,7 @@ def test_hoisted_libm_calls_use_the_reference_libm_and_expensive_columns_get_a_p
             if m == "egno" and g == "cmp":
                 all_src = cudagen.ModelProgram(prog.unit, libm="glibc-all").groups[g].cuda_source(m)
                 loop = all_src[all_src.index("#pragma unroll 1"):]
-                assert "inflx_gl_pow(" in loop[: loop.index("inflx_grid_complete_analysis_sweep")]
+                assert "inflx_gl_pow_m(" in loop[: loop.index("inflx_grid_complete_analysis_sweep")]
     assert progs["d5"].groups["cmp"].cols_prepass and not progs["egno"].groups["cmp"].cols_prepass
     gp = progs["d5"].groups["cmp"]
     src = gp.cuda_source("d5")
